@@ -1,0 +1,140 @@
+/*
+ * lidar_snow_sim.h -- C ABI of the B200-native LiDAR snowfall / wet-ground augmentation engine.
+ *
+ * The reference (SysCV/LiDAR_snow_sim) has no FFI: its boundary is plain Python functions on NumPy arrays
+ * (SURVEY.md 8b).  This header is what a binding for that boundary would bind; lidar_snow_sim_b200/_lib.py is the
+ * ctypes binding and lidar_snow_sim_b200/snowfall/simulation.py mirrors the reference signatures on top of it.
+ * Each entry point cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns an lss_status (0 = LSS_OK); lss_last_error() gives a human-readable message;
+ *   - "d_" pointers are DEVICE pointers on the engine's device, "h_" pointers are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device work of a call is
+ *     enqueued on it and the call returns without synchronising unless stated otherwise;
+ *   - clouds are float32 rows (x, y, z, intensity, channel), the STF / reference layout (tools/snowfall/precompute.py:78);
+ *   - no torch / C++ types cross this boundary.
+ */
+#ifndef LIDAR_SNOW_SIM_H
+#define LIDAR_SNOW_SIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LSS_API __attribute__((visibility("default")))
+#else
+#define LSS_API
+#endif
+
+typedef struct lss_engine lss_engine;
+
+typedef enum {
+    LSS_OK = 0,
+    LSS_ERR_INVALID_ARG = 1,
+    LSS_ERR_CUDA = 2,
+    LSS_ERR_NO_TABLE = 3,         /* FileNotFoundError analogue: particle table set not uploaded (simulation.py:329) */
+    LSS_ERR_RANGE_INDEX = 4,      /* IndexError analogue: a waveform sample index >= 1230, i.e. a return beyond
+                                     ~120 m on a beam that has occluders (simulation.py:149) */
+    LSS_ERR_NEGATIVE_INTENSITY = 5,  /* AssertionError analogue (simulation.py:184) */
+    LSS_ERR_OCCLUDER_OVERFLOW = 6,   /* more occluders on one beam than the engine's per-beam capacity */
+    LSS_ERR_WORKSPACE = 7,        /* caller-supplied workspace too small */
+    LSS_ERR_NO_SENSOR = 8         /* AssertionError analogue: sensor constants missing (simulation.py:35,474-480) */
+} lss_status;
+
+/* flags for lss_snowfall_batch */
+#define LSS_FLAG_THRESHOLD_FILTER 0x1u   /* apply keep = (label==2) | (round(I) > threshold(d))  (simulation.py:516-523) */
+#define LSS_FLAG_CAMERA_FOV 0x2u         /* apply the camera field-of-view filter (simulation.py:532-540) */
+#define LSS_FLAG_DEVICE_PREPASS 0x4u     /* compute ground plane + noise-threshold polynomial on the device
+                                            (simulation.py:449-467) instead of taking h_thresh_poly */
+#define LSS_FLAG_ASSUME_SORTED 0x8u      /* input clouds are already grouped by channel (skips simulation.py:447) */
+
+#define LSS_N_CHANNELS 64
+#define LSS_POINT_STRIDE 5
+
+/* ---- lifetime -------------------------------------------------------------------------------------------------- */
+LSS_API lss_status lss_create(int device, lss_engine **out);
+LSS_API void lss_destroy(lss_engine *e);
+LSS_API const char *lss_status_string(lss_status s);
+LSS_API const char *lss_last_error(const lss_engine *e);
+LSS_API int lss_version(void);
+
+/* ---- sensor constants ------------------------------------------------------------------------------------------
+ * Replaces the YAML read of calib/20171102_64E_S3.yaml (simulation.py:474-480) and the per-channel lookups at
+ * simulation.py:72-76 (min_intensity default 0, focal_distance [m as in the YAML], focal_slope) and :123-126
+ * (max_intensity 255, or 230 for channels 53/55/56/58).  All arrays: n_channels doubles, host.                    */
+LSS_API lss_status lss_set_sensor(lss_engine *e, int n_channels, const double *h_focal_distance, const double *h_focal_slope,
+                          const double *h_min_intensity, const double *h_max_intensity);
+
+/* Camera calibration for the FOV filter: replaces get_calib() (simulation.py:32-36) +
+ * lib/OpenPCDet/pcdet/utils/calibration_kitti.py:5-20.  Row-major float32: P2[3*4], R0[3*3], V2C[3*4].            */
+LSS_API lss_status lss_set_camera(lss_engine *e, const float *h_P2, const float *h_R0, const float *h_V2C, int img_h,
+                          int img_w);
+
+/* ---- particle tables ---------------------------------------------------------------------------------------------
+ * Replaces np.load('<prefix>_<k>.npy') per channel (simulation.py:78,324-329).  One "table set" = the n_planes
+ * (x, y, r) float64 tables of one particle_file_prefix; plane k (file index k+1) is rows
+ * h_plane_offsets[k] .. h_plane_offsets[k+1] of h_xyr.  The set is preprocessed on the device into an
+ * azimuth-bucketed, range-sorted candidate index and stays resident (L2-sized) until freed.
+ * max_beam_divergence_rad bounds the beam_divergence later calls may use with this set.
+ * Synchronises the stream before returning (the host arrays may be released afterwards).                           */
+LSS_API lss_status lss_upload_particles(lss_engine *e, int n_planes, const double *h_xyr, const int64_t *h_plane_offsets,
+                                double max_beam_divergence_rad, int n_azimuth_buckets, void *stream,
+                                int *table_id_out);
+/* same, from device-resident tables (e.g. written by lss_sample_particles) */
+LSS_API lss_status lss_upload_particles_device(lss_engine *e, int n_planes, const double *d_xyr,
+                                       const int64_t *h_plane_offsets, double max_beam_divergence_rad,
+                                       int n_azimuth_buckets, void *stream, int *table_id_out);
+LSS_API lss_status lss_free_particles(lss_engine *e, int table_id);
+/* bytes of device memory held by a table set, and its number of candidate-index entries */
+LSS_API lss_status lss_table_info(lss_engine *e, int table_id, int64_t *n_particles, int64_t *n_entries, int64_t *bytes);
+
+/* ---- snowfall augmentation ---------------------------------------------------------------------------------------
+ * Batched augment() (simulation.py:427-544) on device-resident clouds.
+ *
+ *   d_points         float32[n_total*5]   clouds concatenated; cloud b = rows h_cloud_offsets[b] .. [b+1]
+ *   h_cloud_offsets  int64[n_clouds+1]    host
+ *   h_order          int32[n_clouds*64]   channel -> plane index per cloud: the `order` list of simulation.py:483-486
+ *                                         (the caller owns the random.shuffle so results are reproducible)
+ *   beam_divergence_deg                   as in the reference (degrees; callers pass degrees(3e-3))
+ *   d_theta          float32[n_total] or NULL.  Optional beam azimuths atan2(y,x) in ORIGINAL row order.  The
+ *                                         reference's float32 np.arctan2 is host/SIMD dependent;
+ *                                         parity harnesses pass the oracle host's bits here.  NULL: computed on
+ *                                         device as the correctly rounded float32 of the float64 atan2.
+ *   h_thresh_poly    float64[n_clouds*3] or NULL: np.polyfit coefficients p of simulation.py:467-469 per cloud
+ *                                         (required with LSS_FLAG_THRESHOLD_FILTER unless LSS_FLAG_DEVICE_PREPASS)
+ *   noise_floor                           simulation.py:428 (used by the device pre-pass only)
+ *   flags                                 LSS_FLAG_*
+ *   d_out_points     float32[n_total*5]   augmented rows (x, y, z, intensity, label), channel-sorted, cloud b
+ *                                         compacted to the front of its own slot: rows h_cloud_offsets[b] ..
+ *                                         h_cloud_offsets[b] + count[b]; rows behind that are unspecified
+ *   d_out_counts     int32[n_clouds]      rows kept per cloud
+ *   d_out_stats      float64[n_clouds*4]  num_attenuated, num_removed, avg_intensity_diff, intensity_diff_sum
+ *                                         (simulation.py:525-542)
+ *   d_out_full       float32[n_total*5] or NULL: optional un-filtered channel-sorted rows (label column filled)
+ *   d_out_perm       int32[n_total] or NULL: optional original row index (within its cloud) of each sorted row
+ *   d_out_nocc       int32[n_total] or NULL: optional number of claiming occluders per (sorted) beam
+ *   d_workspace / workspace_bytes         scratch; query the size with lss_snowfall_workspace_bytes
+ *
+ * Errors raised by the device (LSS_ERR_RANGE_INDEX, ...) are latched in the engine and reported by
+ * lss_check_async() after the stream has been synchronised by the caller.                                          */
+LSS_API lss_status lss_snowfall_batch(lss_engine *e, int table_id, const float *d_points, const int64_t *h_cloud_offsets,
+                              int n_clouds, const int32_t *h_order, double beam_divergence_deg, const float *d_theta,
+                              const double *h_thresh_poly, double noise_floor, uint32_t flags, float *d_out_points,
+                              int32_t *d_out_counts, double *d_out_stats, float *d_out_full, int32_t *d_out_perm,
+                              int32_t *d_out_nocc, void *d_workspace, int64_t workspace_bytes, void *stream);
+LSS_API int64_t lss_snowfall_workspace_bytes(int64_t n_total, int n_clouds);
+/* Synchronises `stream`, then returns and clears the latched asynchronous device status.                          */
+LSS_API lss_status lss_check_async(lss_engine *e, void *stream);
+/* number of kernel launches the engine has enqueued since creation (bench.py's gpu_launches) */
+LSS_API int64_t lss_launch_count(const lss_engine *e);
+/* test hook: the engine's range grid R = np.round(np.linspace(0, 120 + c*tau_h, 1230), 2) (simulation.py:111-116),
+ * 1230 doubles written to h_out.  Host only, needs no GPU.                                                          */
+LSS_API lss_status lss_debug_range_grid(double *h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDAR_SNOW_SIM_H */

@@ -1,0 +1,189 @@
+"""
+SnowfallEngine -- thin host-side owner of one C-ABI engine (one GPU).  PyTorch is used only as the device container
+(tensors, streams); all arithmetic happens in liblss_b200.so.
+
+One process per GPU: create one engine per rank; clouds are independent, so a batch shards across ranks with no
+data-path collective (see lidar_snow_sim_b200/distributed.py for the gather of the augmented batch).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .calib.hdl64e_s3 import sensor_arrays
+
+DEFAULT_MAX_DIVERGENCE_RAD = 3e-3          # callers pass beam_divergence = degrees(3e-3) (precompute.py:104)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        return ctypes.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+class SnowfallEngine:
+    def __init__(self, device=0, sensor_table=None, camera=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('SnowfallEngine needs a CUDA device (no CPU fallback)')
+        self.device = torch.device('cuda', device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.lss_create(device, ctypes.byref(h)))
+        self.h = h
+        fd, fs, mi, mx = sensor_arrays(sensor_table)
+        self._sensor = [np.ascontiguousarray(a, dtype=np.float64) for a in (fd, fs, mi, mx)]
+        _lib.check(self.lib.lss_set_sensor(self.h, len(fd), *[_ptr(a) for a in self._sensor]), self.h)
+        if camera is None:
+            from .calib.dense_camera import STF_HDL64_CAMERA as camera
+        self.set_camera(camera)
+        self._tables = {}
+        self._ws = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.lss_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_camera(self, camera):
+        P2 = np.ascontiguousarray(camera['P2'], dtype=np.float32).reshape(3, 4)
+        R0 = np.ascontiguousarray(camera['R0'], dtype=np.float32).reshape(3, 3)
+        V2C = np.ascontiguousarray(camera['V2C'], dtype=np.float32).reshape(3, 4)
+        h, w = camera.get('img_shape', (1024, 1920))
+        _lib.check(self.lib.lss_set_camera(self.h, _ptr(P2), _ptr(R0), _ptr(V2C), int(h), int(w)), self.h)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def upload_tables(self, tables, max_beam_divergence_rad=DEFAULT_MAX_DIVERGENCE_RAD, n_buckets=2048):
+        """tables: sequence of float64 (Np_k, 3) arrays (x, y, r); plane index k <-> file '<prefix>_<k+1>.npy'."""
+        off = np.zeros(len(tables) + 1, dtype=np.int64)
+        for k, t in enumerate(tables):
+            t = np.asarray(t)
+            if t.ndim != 2 or t.shape[1] != 3:
+                raise ValueError('particle table must be (N, 3)')
+            off[k + 1] = off[k] + t.shape[0]
+        xyr = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t in tables], axis=0))
+        tid = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lss_upload_particles(self.h, len(tables), _ptr(xyr), _ptr(off),
+                                                     float(max_beam_divergence_rad), int(n_buckets), self._stream(),
+                                                     ctypes.byref(tid)), self.h)
+        self._tables[tid.value] = dict(n_planes=len(tables), max_div=float(max_beam_divergence_rad))
+        return tid.value
+
+    def upload_tables_device(self, xyr, plane_offsets, max_beam_divergence_rad=DEFAULT_MAX_DIVERGENCE_RAD,
+                             n_buckets=2048):
+        """xyr: CUDA float64 tensor (sum Np, 3); plane_offsets: int64 host array (n_planes + 1)."""
+        off = np.ascontiguousarray(plane_offsets, dtype=np.int64)
+        assert xyr.is_cuda and xyr.dtype == torch.float64 and xyr.is_contiguous()
+        tid = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lss_upload_particles_device(self.h, len(off) - 1, _ptr(xyr), _ptr(off),
+                                                            float(max_beam_divergence_rad), int(n_buckets),
+                                                            self._stream(), ctypes.byref(tid)), self.h)
+        self._tables[tid.value] = dict(n_planes=len(off) - 1, max_div=float(max_beam_divergence_rad))
+        return tid.value
+
+    def free_tables(self, table_id):
+        _lib.check(self.lib.lss_free_particles(self.h, int(table_id)), self.h)
+        self._tables.pop(table_id, None)
+
+    def table_info(self, table_id):
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.lib.lss_table_info(self.h, int(table_id), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+                   self.h)
+        return dict(n_particles=a.value, n_entries=b.value, bytes=c.value)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _workspace(self, n_total, n_clouds):
+        need = self.lib.lss_snowfall_workspace_bytes(int(n_total), int(n_clouds))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    def snowfall_batch(self, table_id, points, cloud_offsets, order, beam_divergence_deg, theta=None,
+                       thresh_poly=None, noise_floor=0.7, threshold_filter=True, camera_fov=False,
+                       device_prepass=False, assume_sorted=False, want_full=False, want_perm=False, want_nocc=False,
+                       out=None):
+        """
+        Batched augment() on device-resident clouds (enqueued on torch's current stream, no synchronisation).
+
+        points: CUDA float32 (N, 5); cloud_offsets: int64 host array (B + 1); order: int32 host (B, 64).
+        Returns dict(points=(N,5) slot-compacted rows, counts=(B,), stats=(B,4) [, full, perm, nocc]).
+        Call `check()` (synchronises) to surface asynchronous device errors.
+        """
+        assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous()
+        off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
+        B = off.shape[0] - 1
+        N = int(off[-1])
+        assert points.shape[0] == N and points.shape[1] == 5
+        order = np.ascontiguousarray(order, dtype=np.int32).reshape(B, 64)
+        flags = 0
+        if threshold_filter:
+            flags |= _lib.FLAG_THRESHOLD_FILTER
+        if camera_fov:
+            flags |= _lib.FLAG_CAMERA_FOV
+        if device_prepass:
+            flags |= _lib.FLAG_DEVICE_PREPASS
+        if assume_sorted:
+            flags |= _lib.FLAG_ASSUME_SORTED
+        tp = None
+        if thresh_poly is not None:
+            tp = np.ascontiguousarray(thresh_poly, dtype=np.float64).reshape(B, 3)
+        if theta is not None:
+            assert theta.is_cuda and theta.dtype == torch.float32 and theta.shape[0] == N
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = {}
+            if 'points' not in out:
+                out['points'] = torch.empty((N, 5), dtype=torch.float32, device=self.device)
+                out['counts'] = torch.empty((B,), dtype=torch.int32, device=self.device)
+                out['stats'] = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+            if want_full and 'full' not in out:
+                out['full'] = torch.empty((N, 5), dtype=torch.float32, device=self.device)
+            if want_perm and 'perm' not in out:
+                out['perm'] = torch.empty((N,), dtype=torch.int32, device=self.device)
+            if want_nocc and 'nocc' not in out:
+                out['nocc'] = torch.empty((N,), dtype=torch.int32, device=self.device)
+            ws, need = self._workspace(N, B)
+            st = self.lib.lss_snowfall_batch(
+                self.h, int(table_id), _ptr(points), _ptr(off), B, _ptr(order), float(beam_divergence_deg),
+                _ptr(theta), _ptr(tp), float(noise_floor), flags, _ptr(out['points']), _ptr(out['counts']),
+                _ptr(out['stats']), _ptr(out.get('full')) if want_full else None,
+                _ptr(out.get('perm')) if want_perm else None, _ptr(out.get('nocc')) if want_nocc else None,
+                _ptr(ws), int(ws.numel()), self._stream())
+        _lib.check(st, self.h)
+        return out
+
+    def check(self):
+        """Synchronise the current stream and raise the exception type the reference would have raised."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lss_check_async(self.h, self._stream()), self.h)
+
+    def launch_count(self):
+        return int(self.lib.lss_launch_count(self.h))
+
+
+_default_engines = {}
+
+
+def default_engine(device=None):
+    """Process-wide engine per device, created on first use (used by the reference-signature wrappers)."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if device not in _default_engines:
+        _default_engines[device] = SnowfallEngine(device)
+    return _default_engines[device]

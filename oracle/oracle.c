@@ -432,3 +432,18 @@ int orc_max_threads(void)
     return 1;
 #endif
 }
+
+/* test hook: compute_occlusion_dict (simulation.py:231-295) on caller-supplied intervals (already sorted by distance).
+ * intervals: L rows (a1, a2, dist).  Writes up to L+1 (r, ratio) pairs, the hard target last; returns the count. */
+int orc_occlusion_dict(double right, double left, const double *intervals, int L, double current_range,
+                       double beam_divergence_deg, double *out_r, double *out_ratio)
+{
+    interval_t *iv = (interval_t *)malloc(sizeof(interval_t) * (L > 0 ? L : 1));
+    double *work = (double *)malloc(sizeof(double) * 3 * (2 * L + 2));
+    int *iwork = (int *)malloc(sizeof(int) * (2 * L + 2));
+    for (int j = 0; j < L; j++) { iv[j].a1 = intervals[3 * j]; iv[j].a2 = intervals[3 * j + 1]; iv[j].dist = intervals[3 * j + 2]; }
+    int n = 0;
+    occlusion_dict(right, left, iv, L, current_range, beam_divergence_deg, out_r, out_ratio, &n, work, iwork);
+    free(iv); free(work); free(iwork);
+    return n;
+}

@@ -51,6 +51,9 @@ def lib():
         L.orc_snow_channel.argtypes = [ctypes.c_int, f32p, f32p, f32p, f32p, f32p, ctypes.c_int, f64p,
                                        ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_double, f64p, f32p, f64p, i32p, f32p]
+        L.orc_occlusion_dict.restype = ctypes.c_int
+        L.orc_occlusion_dict.argtypes = [ctypes.c_double, ctypes.c_double, f64p, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_double, f64p, f64p]
         _LIB = L
     return _LIB
 
@@ -166,6 +169,20 @@ def snow_channel(points, particles, beam_divergence_deg, focal_distance, focal_s
     if rc != 0:
         raise ERR_NAMES.get(rc, RuntimeError)(f'oracle error {rc}')
     return out, s.value, nocc, th_out
+
+
+def occlusion_dict(beam_angles, intervals, current_range, beam_divergence_deg):
+    """compute_occlusion_dict (simulation.py:231-295).  Returns a list of (key, r, ratio); key -1 = hard target.
+    Keys of claiming particles are their row index in `intervals` is NOT tracked: they are numbered 0.. in dict order
+    of the claiming subset, so compare values in order."""
+    iv = np.ascontiguousarray(intervals, dtype=np.float64).reshape(-1, 3)
+    L = iv.shape[0]
+    r = np.zeros(L + 1)
+    ratio = np.zeros(L + 1)
+    n = lib().orc_occlusion_dict(float(beam_angles[0]), float(beam_angles[1]), _p(iv, ctypes.c_double), L,
+                                 float(current_range), float(beam_divergence_deg), _p(r, ctypes.c_double),
+                                 _p(ratio, ctypes.c_double))
+    return [(float(r[k]), float(ratio[k])) for k in range(n)]
 
 
 def snow_cloud(pc_sorted, tables, order, sensor, beam_divergence_deg, theta=None, threads=None):

@@ -1,0 +1,274 @@
+"""
+GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against
+  (1) the golden vectors frozen from the unmodified reference (tests/golden/),
+  (2) the CPU oracle on the same seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full batch size.
+Bar: labels (the occluded-point mask), integer intensities and the keep mask exact; xyz within 1e-4 relative
+(in practice bit-identical).  The beam azimuth theta is injected where exact-mask parity is asserted, because the
+reference's float32 arctan2 is host dependent; the device-computed theta is checked separately.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import DIV, canon, channel_case, augment_case
+from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
+from lidar_snow_sim_b200.synthetic import synthetic_cloud, synthetic_particles
+
+pytestmark = pytest.mark.gpu
+
+
+def run_full(engine, tid, pc, order, theta=None, thresh_poly=None, **kw):
+    """Un-filtered, channel-sorted rows + perm + occluder counts for one cloud."""
+    d_pc = torch.from_numpy(np.ascontiguousarray(pc, dtype=np.float32)).cuda()
+    d_th = None if theta is None else torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float32)).cuda()
+    off = np.array([0, pc.shape[0]], dtype=np.int64)
+    res = engine.snowfall_batch(tid, d_pc, off, np.asarray(order, dtype=np.int32)[None], DIV, theta=d_th,
+                                thresh_poly=thresh_poly, threshold_filter=thresh_poly is not None, want_full=True,
+                                want_perm=True, want_nocc=True, **kw)
+    engine.check()
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+def assert_rows_match(got, want, what=''):
+    assert got.shape == want.shape, what
+    assert np.array_equal(got[:, 4], want[:, 4]), f'{what}: label mask differs'
+    assert np.array_equal(got[:, 3], want[:, 3]), f'{what}: intensities differ'
+    rel = np.abs(got[:, :3] - want[:, :3]) / np.maximum(np.abs(want[:, :3]), 1e-6)
+    assert rel.max() <= 1e-4, f'{what}: xyz off by {rel.max()}'
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (1) golden vectors from the reference
+# ----------------------------------------------------------------------------------------------------------------------
+def test_golden_kat_channel(engine, gold_dir):
+    g = np.load(os.path.join(gold_dir, 'kat_channel.npz'))
+    tid = engine.upload_tables([g['particles']] * 64)
+    r = run_full(engine, tid, g['points'], list(range(64)), theta=g['theta'])
+    engine.free_tables(tid)
+    assert np.array_equal(r['full'], g['out'])              # all points are channel 2: sorted order == input order
+    assert r['stats'][0, 3] == float(g['intensity_diff_sum'])
+    assert np.array_equal(r['nocc'], g['n_occluders'])
+
+
+def test_golden_channel_cases(engine, gold_dir):
+    rec = np.load(os.path.join(gold_dir, 'channel_cases.npz'))
+    for ci in range(int(rec['n_cases'])):
+        table = channel_case(rec, ci)
+        tid = engine.upload_tables([table] * 64)
+        r = run_full(engine, tid, rec[f'c{ci}_points'], list(range(64)), theta=rec[f'c{ci}_theta'])
+        engine.free_tables(tid)
+        assert np.array_equal(r['full'], rec[f'c{ci}_out']), f'case {ci}'
+        assert r['stats'][0, 3] == float(rec[f'c{ci}_sum'])
+        assert np.array_equal(r['nocc'], rec[f'c{ci}_nocc'])
+
+
+@pytest.mark.parametrize('name', ['augment_a', 'augment_b'])
+def test_golden_augment_api(engine, gold_dir, name):
+    """The reference-signature wrapper end to end (threshold polynomial injected from the reference run)."""
+    from lidar_snow_sim_b200.snowfall.simulation import augment
+    g = np.load(os.path.join(gold_dir, f'{name}.npz'))
+    pc, tables = augment_case(g)
+    stats, aug = augment(pc, 'unused', DIV, only_camera_fov=bool(g['fov']), engine=engine, tables=tables,
+                         order=g['order'].tolist(), thresh_poly=g['thresh_poly'], theta=g['theta'])
+    assert stats == tuple(int(v) for v in g['stats'])
+    assert aug.dtype == np.float32
+    assert np.array_equal(canon(aug), g['out'])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (2) against the oracle on seeded inputs
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def tables18k():
+    return [synthetic_particles(7000 + k, 18000) for k in range(64)]
+
+
+def test_vs_oracle_cloud(engine, oracle, tables18k):
+    rng = np.random.default_rng(5)
+    pc = synthetic_cloud(seed=5, n_azimuth=384, drop=0.08, shuffle_rows=True)
+    order = rng.permutation(64).tolist()
+    poly = np.array([1e-3, -0.2, 14.0])
+    idx = pc[:, 4].argsort(kind='stable')
+    pcs = pc[idx]
+    o_stats, o_aug, oi = oracle.augment(pc, tables18k, DIV, sensor_arrays(), order=order, thresh_poly=poly,
+                                        stable_sort=True, return_internals=True)
+    tid = engine.upload_tables(tables18k)
+    theta_orig = np.empty(pc.shape[0], dtype=np.float32)
+    theta_orig[idx] = oi['theta']                          # oracle host's atan2f bits, back in original row order
+    r = run_full(engine, tid, pc, order, theta=theta_orig, thresh_poly=poly)
+    assert np.array_equal(r['perm'], idx)                  # stable channel sort
+    full_o = oi['full']
+    assert_rows_match(r['full'], full_o, 'vs oracle')
+    assert np.array_equal(r['full'], full_o)               # in practice bit-identical
+    assert np.array_equal(r['nocc'], oi['n_occluders'])
+    n = int(r['counts'][0])
+    assert np.array_equal(r['points'][:n], o_aug)
+    assert (int(r['stats'][0, 0]), int(r['stats'][0, 1]), int(r['stats'][0, 2])) == o_stats
+    assert r['stats'][0, 3] == oi['intensity_diff_sum']
+
+    # device-computed theta (correctly rounded float32 of the float64 atan2): the only differences allowed are beams
+    # whose azimuth differs by an ulp from the host libm's atan2f -- report and bound the mismatch rate
+    r2 = run_full(engine, tid, pc, order, thresh_poly=poly)
+    mism = (r2['full'][:, 4] != full_o[:, 4]).mean()
+    print(f'label mismatch rate with device theta: {mism:.2e}')
+    assert mism < 2e-3
+    th64 = np.arctan2(pcs[:, 1].astype(np.float64), pcs[:, 0].astype(np.float64)).astype(np.float32)
+    same_theta = th64 == oi['theta']
+    assert np.array_equal(r2['full'][same_theta], full_o[same_theta])
+    engine.free_tables(tid)
+
+
+def test_batch_ragged_and_empty(engine, oracle, tables18k):
+    """Ragged batch with an empty cloud, a tiny cloud and rows with invalid channel ids."""
+    clouds = [synthetic_cloud(seed=20, n_azimuth=64), np.zeros((0, 5), np.float32),
+              synthetic_cloud(seed=21, n_azimuth=96, shuffle_rows=True)[:777], synthetic_cloud(seed=22, n_azimuth=32)]
+    clouds[3] = clouds[3].copy()
+    clouds[3][5, 4] = 64.0          # not a channel: passes through untouched
+    clouds[3][9, 4] = 7.5
+    clouds[3][11, 4] = -1.0
+    rng = np.random.default_rng(9)
+    orders = np.stack([rng.permutation(64) for _ in clouds]).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+    pts = torch.from_numpy(np.concatenate(clouds)).cuda()
+    tid = engine.upload_tables(tables18k)
+    th = []
+    want = []
+    for c, o in zip(clouds, orders):
+        if c.shape[0] == 0:
+            want.append(np.zeros((0, 5), np.float32))
+            th.append(np.zeros(0, np.float32))
+            continue
+        idx = c[:, 4].argsort(kind='stable')
+        cs = c[idx]
+        aug, s, nocc, theta = oracle.snow_cloud(cs, tables18k, o.tolist(), sensor_arrays(), DIV)
+        aug[:, 3] = np.round(aug[:, 3])
+        want.append(aug)
+        t = np.empty(c.shape[0], np.float32)
+        t[idx] = theta
+        th.append(t)
+    theta = torch.from_numpy(np.concatenate(th)).cuda()
+    res = engine.snowfall_batch(tid, pts, off, orders, DIV, theta=theta, threshold_filter=False, want_full=True)
+    engine.check()
+    full = res['full'].cpu().numpy()
+    counts = res['counts'].cpu().numpy()
+    for b, c in enumerate(clouds):
+        got = full[off[b]:off[b + 1]]
+        valid = (want[b][:, 4] >= 0) if got.shape[0] else np.zeros(0, bool)
+        assert counts[b] == c.shape[0]                      # no filter: everything kept
+        if got.shape[0] == 0:
+            continue
+        # rows with an invalid channel id sort to the end (stable) and keep the channel value in column 4
+        cs = c[c[:, 4].argsort(kind='stable')]
+        ok_ch = (cs[:, 4] >= 0) & (cs[:, 4] < 64) & (cs[:, 4] == np.floor(cs[:, 4]))
+        n_ok = int(ok_ch.sum())
+        good = canon(want[b][ok_ch])
+        assert np.array_equal(canon(got[:n_ok]), good)
+        bad_rows = got[n_ok:]
+        assert bad_rows.shape[0] == (~ok_ch).sum()
+        assert np.array_equal(canon(bad_rows), canon(cs[~ok_ch]))
+        assert np.array_equal(res['points'].cpu().numpy()[off[b]:off[b] + counts[b]], got)
+    engine.free_tables(tid)
+
+
+def test_errors(engine, tables18k):
+    from lidar_snow_sim_b200.snowfall.simulation import augment
+    tid = engine.upload_tables(tables18k[:8] * 8)
+    pc = synthetic_cloud(seed=1, n_azimuth=64)
+    far = pc.copy()
+    far[:, :3] *= (125.0 / np.linalg.norm(far[:, :3], axis=1))[:, None]      # every return beyond the 1230-sample grid
+    with pytest.raises(IndexError):                                          # simulation.py:149
+        run_full(engine, tid, far, list(range(64)))
+    r = run_full(engine, tid, pc, list(range(64)))                           # engine still usable afterwards
+    assert set(np.unique(r['full'][:, 4])) <= {0.0, 1.0, 2.0}
+    with pytest.raises(FileNotFoundError):                                   # simulation.py:329
+        augment(pc, 'no_such_prefix', DIV, root_path='/nonexistent', engine=engine)
+    with pytest.raises(FileNotFoundError):
+        engine.snowfall_batch(tid, torch.from_numpy(pc).cuda(), np.array([0, pc.shape[0]]), np.full((1, 64), 99), DIV,
+                              threshold_filter=False)
+    with pytest.raises(ValueError):                                          # divergence beyond what the index was built for
+        engine.snowfall_batch(tid, torch.from_numpy(pc).cuda(), np.array([0, pc.shape[0]]),
+                              np.arange(64)[None], float(np.degrees(1e-2)), threshold_filter=False)
+    engine.free_tables(tid)
+    with pytest.raises(FileNotFoundError):
+        engine.free_tables(tid)
+
+
+def test_wider_beam_and_bucket_counts(engine, oracle):
+    """Other beam divergences / index resolutions give the same answers (index is a pure accelerator)."""
+    tables = [synthetic_particles(300 + k, 9000) for k in range(64)]
+    pc = synthetic_cloud(seed=8, n_azimuth=96)
+    div = float(np.degrees(6e-3))
+    aug, s, nocc, theta = oracle.snow_cloud(pc, tables, list(range(64)), sensor_arrays(), div)
+    aug[:, 3] = np.round(aug[:, 3])
+    for nb in (512, 2048, 8192):
+        tid = engine.upload_tables(tables, max_beam_divergence_rad=6e-3, n_buckets=nb)
+        d_pc = torch.from_numpy(pc).cuda()
+        res = engine.snowfall_batch(tid, d_pc, np.array([0, pc.shape[0]]), np.arange(64)[None], div,
+                                    theta=torch.from_numpy(theta).cuda(), threshold_filter=False, want_full=True,
+                                    want_nocc=True, assume_sorted=True)
+        engine.check()
+        assert np.array_equal(res['full'].cpu().numpy(), aug), f'n_buckets={nb}'
+        assert np.array_equal(res['nocc'].cpu().numpy(), nocc)
+        engine.free_tables(tid)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (3) full-size properties (BASELINE.json config 1/2: batch of 64 x 2048 clouds)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_full_size_properties(engine, tables18k):
+    B = 8
+    clouds = [synthetic_cloud(seed=100 + b) for b in range(B)]
+    N = clouds[0].shape[0]
+    assert N == 64 * 2048
+    pts = torch.from_numpy(np.concatenate(clouds)).cuda()
+    off = (np.arange(B + 1) * N).astype(np.int64)
+    rng = np.random.default_rng(3)
+    orders = np.stack([rng.permutation(64) for _ in range(B)]).astype(np.int32)
+    poly = np.tile(np.array([2e-3, -0.3, 12.0]), (B, 1))
+    tid = engine.upload_tables(tables18k)
+    r1 = engine.snowfall_batch(tid, pts, off, orders, DIV, thresh_poly=poly, want_full=True, want_perm=True)
+    engine.check()
+    r1 = {k: v.clone() for k, v in r1.items()}
+    r2 = engine.snowfall_batch(tid, pts, off, orders, DIV, thresh_poly=poly, want_full=True, want_perm=True)
+    engine.check()
+    # determinism / idempotence of the whole pipeline
+    for k in ('full', 'counts', 'stats', 'perm'):
+        assert torch.equal(r1[k], r2[k]), k
+    full = r1['full'].cpu().numpy().reshape(B, N, 5)
+    counts = r1['counts'].cpu().numpy()
+    stats = r1['stats'].cpu().numpy()
+    src = np.stack(clouds)
+    perm = r1['perm'].cpu().numpy().reshape(B, N)
+    for b in range(B):
+        lab = full[b, :, 4]
+        assert set(np.unique(lab)) <= {0.0, 1.0, 2.0}
+        s = src[b][perm[b]]
+        assert np.array_equal(np.sort(perm[b]), np.arange(N))
+        assert np.all(np.diff(s[:, 4]) >= 0)                                 # sorted by channel
+        un = lab == 0
+        assert np.array_equal(full[b][un][:, :3], s[un][:, :3])              # untouched beams keep xyz
+        assert np.array_equal(full[b][un][:, 3], np.round(s[un][:, 3]))
+        att = lab == 1
+        assert np.array_equal(full[b][att][:, :3], s[att][:, :3])            # attenuated: only intensity changes
+        sc = lab == 2
+        d0 = np.linalg.norm(s[sc][:, :3].astype(np.float64), axis=1)
+        d1 = np.linalg.norm(full[b][sc][:, :3].astype(np.float64), axis=1)
+        assert np.all(d1 < d0)                                               # scattered points move towards the sensor
+        cosang = np.sum(s[sc][:, :3].astype(np.float64) * full[b][sc][:, :3], axis=1) / (d0 * d1)
+        assert np.all(cosang > 1 - 1e-6)                                     # ... along the beam
+        assert counts[b] + stats[b, 1] == N                                  # kept + removed == input
+        kept = r1['points'].cpu().numpy()[off[b]:off[b] + counts[b]]
+        assert (kept[:, 4] == 1).sum() == stats[b, 0]
+        # a single-cloud call gives the same rows as the batched call (clouds are independent)
+    rs = engine.snowfall_batch(tid, pts[off[3]:off[4]].contiguous(), np.array([0, N]), orders[3:4], DIV,
+                               thresh_poly=poly[3:4], want_full=True)
+    engine.check()
+    assert torch.equal(rs['full'], r1['full'][off[3]:off[4]])
+    assert int(rs['counts'][0]) == counts[3]
+    frac = [(full[..., 4] == l).mean() for l in (0, 1, 2)]
+    print('label fractions', frac)
+    assert frac[1] > 0.05 and frac[2] > 0.005
+    engine.free_tables(tid)
