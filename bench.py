@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""
+bench.py -- snowfall augmentation throughput on B200 (BASELINE.json metric: augmented LiDAR points/s).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                     # our arm (CUDA engine)
+    python bench.py --impl reference --steps 2 --warmup 1              # CPU arm: the oracle port on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                          # N ranks, one per GPU, weak scaling
+
+Workload (N=1): BASELINE.json configs[1] -- batch = 32 synthetic 64 x 2048 clouds per GPU, snowfall_rate 2.5 mm/h,
+terminal velocity 1.6 m/s, Gunn-Marshall size distribution; tables drawn by the engine's dart-throwing sampler.
+One step = one pass of the whole augment() pipeline over the batch: channel sort, [pre-pass], per-beam solve,
+threshold filter, compaction, stats.  With N > 1 every rank augments its own 32 clouds (clouds are independent, no
+data-path collective) and one NCCL all-gather reassembles the augmented batch on every rank (configs[3]).
+
+`value`     device-resident inputs, CUDA-event time per step on the launching stream, max over ranks
+`e2e`       the public API with pinned HOST buffers: H2D of the batch + augment + D2H of the augmented batch, per step
+`roofline`  the dominant kernel (k_snowfall) against the measured HBM copy peak; algorithmic bytes = 40 B/point
+             + the candidate index it may touch once per launch
+`cpu_baseline`  the CPU oracle port (oracle/) on a bounded sample of the same workload, rank 0, N=1 only
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SNOWFALL_RATE = 2.5
+TERMINAL_VELOCITY = 1.6
+MODE = 'gunn'
+BATCH_PER_GPU = 32
+N_AZIMUTH = 2048
+DIV_DEG = float(np.degrees(3e-3))
+ALGO_BYTES_PER_POINT = 40           # read 5 x f32, write 5 x f32
+FIXED_POLY = (2e-3, -0.3, 12.0)     # only used with --host-threshold
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_workload(rank, batch, seed0=0):
+    from lidar_snow_sim_b200.synthetic import synthetic_cloud
+    clouds = [synthetic_cloud(seed=seed0 + rank * 10000 + b, n_azimuth=N_AZIMUTH) for b in range(batch)]
+    orders = []
+    for b in range(batch):
+        r = random.Random(seed0 + rank * 10000 + b)
+        o = list(range(64))
+        r.shuffle(o)                                # the reference's random.shuffle(order), simulation.py:486
+        orders.append(o)
+    return clouds, np.array(orders, dtype=np.int32)
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (oracle/, restating tools/snowfall/simulation.py) on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    from lidar_snow_sim_b200.snowfall.sampling import sample_table_set
+    from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
+    orc.build()
+    cores = os.cpu_count() or 1
+    tables = sample_table_set(MODE, SNOWFALL_RATE, TERMINAL_VELOCITY, seed=1000)
+    clouds_per_step = args.cpu_clouds
+    clouds, orders = make_workload(0, clouds_per_step)
+    sensor = sensor_arrays()
+    poly = np.array(FIXED_POLY)
+
+    def step():
+        for c, o in zip(clouds, orders):
+            orc.augment(c, tables, DIV_DEG, sensor, order=o.tolist(), thresh_poly=None if not args.host_threshold else poly,
+                        threads=cores, stable_sort=True)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    pts = sum(c.shape[0] for c in clouds)
+    value = pts / dt
+    sample = f'{clouds_per_step} clouds of 64x{N_AZIMUTH} per step ({pts} points), full augment() incl. pre-pass'
+    line = {'impl': 'reference', 'metric': 'augmented LiDAR points/sec', 'value': value, 'unit': 'points/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(args.gpus),
+            'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'clouds_per_s': value / (64 * N_AZIMUTH)}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {'workload': f'BASELINE.json configs[1]: batch={BATCH_PER_GPU} synthetic 64x{N_AZIMUTH} clouds per GPU, '
+                        f'snowfall_rate={SNOWFALL_RATE} mm/h, v={TERMINAL_VELOCITY} m/s, {MODE} DSD, '
+                        f'beam_divergence=3 mrad' + ('' if n_gpus == 1 else f'; x{n_gpus} GPUs + NCCL all-gather of the '
+                                                     f'augmented batch (configs[3])'),
+            'batch_per_gpu': BATCH_PER_GPU, 'points_per_cloud': 64 * N_AZIMUTH, 'parallelism': f'clouds sharded x{n_gpus}',
+            'l2': 'L2 flushed between timed steps by writing a 512 MiB buffer'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU)
+    ap.add_argument('--cpu-clouds', type=int, default=2, help='clouds per step of the CPU arm / cpu_baseline sample')
+    ap.add_argument('--host-threshold', action='store_true',
+                    help='skip the device pre-pass and use a fixed threshold polynomial (debug only; reported in config)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.steps = max(1, args.steps)
+    args.warmup = max(3, args.warmup) if args.impl == 'b200' else max(0, args.warmup)
+
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lidar_snow_sim_b200.engine import SnowfallEngine
+    from lidar_snow_sim_b200.snowfall.sampling import sample_table_set
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback for the b200 arm)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+
+    eng = SnowfallEngine(local_rank)
+    tables = sample_table_set(MODE, SNOWFALL_RATE, TERMINAL_VELOCITY, seed=1000)
+    tid = eng.upload_tables(tables)
+    tinfo = eng.table_info(tid)
+    B = args.batch
+    clouds, orders = make_workload(rank, B)
+    n_per = [c.shape[0] for c in clouds]
+    off = np.concatenate([[0], np.cumsum(n_per)]).astype(np.int64)
+    N = int(off[-1])
+    host_pts = torch.from_numpy(np.concatenate(clouds)).pin_memory()
+    d_pts = host_pts.to(dev)
+    poly = np.tile(np.array(FIXED_POLY), (B, 1)) if args.host_threshold else None
+    device_prepass = not args.host_threshold
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world * N, 5), dtype=torch.float32, device=dev)
+        gathered_counts = torch.empty((world * B,), dtype=torch.int32, device=dev)
+
+    def step(points):
+        r = eng.snowfall_batch(tid, points, off, orders, DIV_DEG, thresh_poly=poly, device_prepass=device_prepass,
+                               out=out)
+        if world > 1:       # one all-gather of the fixed-stride augmented batch + counts
+            dist.all_gather_into_tensor(gathered, r['points'])
+            dist.all_gather_into_tensor(gathered_counts, r['counts'])
+        return r
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step(d_pts)
+    eng.check()
+    eng.set_profiling(True)
+    eng.kernel_times(reset=True)
+    launches0 = eng.launch_count()
+    clocks = ClockSampler(local_rank)
+    sync_all()
+    clocks.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                      # evict the previous step's lines from the 126 MB L2
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(d_pts)
+        e1.record()
+        evs.append((e0, e1))
+    sync_all()
+    clk = clocks.stop()
+    eng.check()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(np.sum(step_ms))
+    launches = eng.launch_count() - launches0
+    ktimes = eng.kernel_times(reset=True)
+    eng.set_profiling(False)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    points_all = N * world
+    value = points_all / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers (`e2e`) --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_out = torch.empty((N, 5), dtype=torch.float32).pin_memory()
+        host_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+        host_stats = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+        d_in = torch.empty_like(d_pts)
+
+        def e2e_step():
+            d_in.copy_(host_pts, non_blocking=True)
+            r = step(d_in)
+            host_out.copy_(r['points'], non_blocking=True)
+            host_counts.copy_(r['counts'], non_blocking=True)
+            host_stats.copy_(r['stats'], non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+            torch.cuda.synchronize(dev)                     # the caller consumes each step's result on the host
+        sync_all()
+        dt = (time.perf_counter() - t0) / args.steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {'value': points_all / dt, 'unit': 'points/s', 'h2d_bytes_per_step': int(N * 20),
+               'd2h_bytes_per_step': int(N * 20 + B * 4 + B * 32), 'ms_per_step': dt * 1e3,
+               'timing': 'host wall clock around H2D + augment + D2H, synchronised every step'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    k_ms, k_calls = ktimes.get('snowfall', (0.0, 0))
+    k_avg_ms = k_ms / max(k_calls, 1)
+    algo_bytes = ALGO_BYTES_PER_POINT * N + tinfo['bytes']
+    achieved = algo_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': 'k_snowfall', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': int(algo_bytes), 'kernel_ms': k_avg_ms,
+                'kernel_share_of_step': k_avg_ms / ms_per_step,
+                'kernel_ms_all': {k: (v[0] / max(v[1], 1)) * (v[1] / args.steps) for k, v in ktimes.items() if v[1]},
+                'note': 'FP64/issue bound, not HBM bound: see DESIGN.md; traffic from ncu is in profiles/'}
+    prof = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(prof):
+        try:
+            roofline['traffic'] = json.load(open(prof)).get('k_snowfall_dram_bytes_per_launch')
+        except Exception:
+            pass
+
+    # ---- CPU baseline (oracle port, bounded sample) ---------------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
+        orc.build()
+        cores = os.cpu_count() or 1
+        sample = clouds[:args.cpu_clouds]
+        t0 = time.perf_counter()
+        for c, o in zip(sample, orders):
+            orc.augment(c, tables, DIV_DEG, sensor_arrays(), order=o.tolist(),
+                        thresh_poly=None if device_prepass else np.array(FIXED_POLY), threads=cores, stable_sort=True)
+        dt = time.perf_counter() - t0
+        cpu = {'value': sum(c.shape[0] for c in sample) / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+               'sample': f'{len(sample)} of the {B} clouds of one step ({sum(c.shape[0] for c in sample)} points), '
+                         f'oracle port (C core + numpy/scipy/sklearn pre-pass), {cores} threads, {dt:.1f} s'}
+
+    cfg = workload_config(args.gpus)
+    cfg['prepass'] = 'device' if device_prepass else 'DEBUG: fixed host-supplied threshold polynomial'
+    cfg['table_particles'] = tinfo['n_particles']
+    cfg['table_index_bytes'] = tinfo['bytes']
+    line = {'metric': 'augmented LiDAR points/sec', 'value': value, 'unit': 'points/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'clouds_per_s': value / (64 * N_AZIMUTH), 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clk,
+            'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -130,6 +130,29 @@ LSS_API int64_t lss_snowfall_workspace_bytes(int64_t n_total, int n_clouds);
 LSS_API lss_status lss_check_async(lss_engine *e, void *stream);
 /* number of kernel launches the engine has enqueued since creation (bench.py's gpu_launches) */
 LSS_API int64_t lss_launch_count(const lss_engine *e);
+/* ---- snowflake table sampler ---------------------------------------------------------------------------------------
+ * dart_throwing(occupancy_ratio, precipitation_rate, R_0, rng, distribution) of tools/snowfall/sampling.py:90-194:
+ * sequential rejection sampling of non-overlapping disks in a disk of radius R_0 until the occupied area reaches
+ * occupancy_ratio * pi * R_0^2.  Host-native (uniform grid instead of the reference's O(N^2) scan); consumes NumPy's
+ * PCG64 stream exactly like the reference, so the same Generator state yields the same table.
+ *   distribution   0 = 'gunn', 1 = 'sekhon'                       (sampling.py:108-113)
+ *   pcg_state      uint64[4] in/out: {state_hi, state_lo, inc_hi, inc_lo} of numpy's PCG64
+ *   h_xyr          float64[capacity*3] out: (x, y, r) rows         n_out: rows written
+ * Needs no GPU.  LSS_ERR_WORKSPACE if `capacity` rows do not suffice.                                               */
+LSS_API lss_status lss_dart_throwing(double occupancy_ratio, double precipitation_rate, double R_0, int distribution,
+                             uint64_t *pcg_state, double *h_xyr, int64_t capacity, int64_t *n_out);
+/* n_planes independent planes (sampling.py:410-413), one host thread per plane up to n_threads (<= 0: all cores).
+ * pcg_states uint64[n_planes*4]; plane k -> h_xyr + 3*k*capacity_per_plane, h_counts[k] rows.                        */
+LSS_API lss_status lss_dart_throwing_planes(int n_planes, double occupancy_ratio, double precipitation_rate, double R_0,
+                                    int distribution, uint64_t *pcg_states, double *h_xyr,
+                                    int64_t capacity_per_plane, int64_t *h_counts, int n_threads);
+
+/* Optional per-kernel timing for bench.py's roofline: when enabled every kernel launch is bracketed by CUDA events
+ * on the launching stream.  lss_kernel_times() (call after synchronising) accumulates and returns, per kernel id
+ * 0..n-1 (names via lss_kernel_name), total milliseconds and number of launches; reset != 0 clears the totals.     */
+LSS_API lss_status lss_set_profiling(lss_engine *e, int enable);
+LSS_API lss_status lss_kernel_times(lss_engine *e, int reset, double *h_ms, int64_t *h_calls, int n);
+LSS_API const char *lss_kernel_name(int kernel);
 /* test hook: the engine's range grid R = np.round(np.linspace(0, 120 + c*tau_h, 1230), 2) (simulation.py:111-116),
  * 1230 doubles written to h_out.  Host only, needs no GPU.                                                          */
 LSS_API lss_status lss_debug_range_grid(double *h_out);

@@ -60,6 +60,13 @@ SIGNATURES = [
     ('lss_check_async', _c.c_int, [_P, _P]),
     ('lss_launch_count', _c.c_int64, [_P]),
     ('lss_debug_range_grid', _c.c_int, [_P]),
+    ('lss_dart_throwing', _c.c_int, [_c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P, _c.c_int64,
+                                     _c.POINTER(_c.c_int64)]),
+    ('lss_dart_throwing_planes', _c.c_int, [_c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P,
+                                            _c.c_int64, _P, _c.c_int]),
+    ('lss_set_profiling', _c.c_int, [_P, _c.c_int]),
+    ('lss_kernel_times', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int]),
+    ('lss_kernel_name', _c.c_char_p, [_c.c_int]),
 ]
 
 _lib = None

@@ -265,6 +265,36 @@ lss_status lss_check_async(lss_engine *e, void *stream)
 
 int64_t lss_launch_count(const lss_engine *e) { return e ? e->launches : 0; }
 
+lss_status lss_set_profiling(lss_engine *e, int enable)
+{
+    if (!e) return LSS_ERR_INVALID_ARG;
+    e->profiling = enable != 0;
+    return LSS_OK;
+}
+
+static const char *kernel_names[LSS_K_COUNT] = {"channel_sort", "prepass", "snowfall", "compact", "finalize", "wet_ground"};
+
+const char *lss_kernel_name(int kernel) { return (kernel >= 0 && kernel < LSS_K_COUNT) ? kernel_names[kernel] : ""; }
+
+lss_status lss_kernel_times(lss_engine *e, int reset, double *h_ms, int64_t *h_calls, int n)
+{
+    if (!e || !h_ms || !h_calls) return LSS_ERR_INVALID_ARG;
+    DeviceGuard g(e->device);
+    for (auto &t : e->timed) {                       // caller has synchronised the stream(s)
+        float ms = 0.0f;
+        if (cudaEventSynchronize(t.end) == cudaSuccess && cudaEventElapsedTime(&ms, t.beg, t.end) == cudaSuccess) {
+            e->kernel_ms[t.kernel] += ms;
+            e->kernel_calls[t.kernel]++;
+        }
+        cudaEventDestroy(t.beg);
+        cudaEventDestroy(t.end);
+    }
+    e->timed.clear();
+    for (int k = 0; k < n && k < LSS_K_COUNT; k++) { h_ms[k] = e->kernel_ms[k]; h_calls[k] = e->kernel_calls[k]; }
+    if (reset) for (int k = 0; k < 16; k++) { e->kernel_ms[k] = 0; e->kernel_calls[k] = 0; }
+    return LSS_OK;
+}
+
 lss_status lss_debug_range_grid(double *h_out)
 {
     if (!h_out) return LSS_ERR_INVALID_ARG;

@@ -71,6 +71,28 @@ struct lss_engine {
     int next_table_id = 1;
     int64_t launches = 0;
     std::string last_error;
+    // optional per-kernel timing (lss_set_profiling): CUDA events on the launching stream around every kernel
+    bool profiling = false;
+    struct TimedLaunch { int kernel; cudaEvent_t beg, end; };
+    std::vector<TimedLaunch> timed;
+    double kernel_ms[16] = {0};
+    int64_t kernel_calls[16] = {0};
+};
+
+enum { LSS_K_SORT = 0, LSS_K_PREPASS = 1, LSS_K_SNOWFALL = 2, LSS_K_COMPACT = 3, LSS_K_FINALIZE = 4, LSS_K_WET = 5,
+       LSS_K_COUNT = 6 };
+
+struct KernelTimer {        // RAII: records begin/end events when profiling is on
+    lss_engine *e; cudaStream_t s; int idx = -1;
+    KernelTimer(lss_engine *e_, int kernel, cudaStream_t s_) : e(e_), s(s_) {
+        e->launches++;
+        if (!e->profiling) return;
+        lss_engine::TimedLaunch t; t.kernel = kernel;
+        cudaEventCreate(&t.beg); cudaEventCreate(&t.end);
+        cudaEventRecord(t.beg, s);
+        e->timed.push_back(t); idx = (int)e->timed.size() - 1;
+    }
+    ~KernelTimer() { if (idx >= 0) cudaEventRecord(e->timed[idx].end, s); }
 };
 
 #define LSS_CUDA_CHECK(e, call)                                                                          \

@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
 
     // ---- cloud-level post: round, threshold, FOV (simulation.py:516-540) ------------------------------------------
     bool keep = active;
+    bool keep_thr = active;      // kept by the threshold filter: num_attenuated is counted BEFORE the FOV filter (:525)
     bool removed = false;
     if (active) {
         out_i = rintf(out_i);
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
             const double thr = __dadd_rn(__dadd_rn(__dmul_rn(p[0], d2), __dmul_rn(p[1], d)), p[2]);
             keep = (out_l == 2.0f) || ((double)out_i > thr);
         }
+        keep_thr = keep;
         if (keep && (a.flags & LSS_FLAG_CAMERA_FOV)) {
             const float *M = a.camera->M, *P2 = a.camera->P2;
             float rx = fmaf(out_z, M[6], fmaf(out_y, M[3], out_x * M[0])) + M[9];
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
         if (a.nocc) a.nocc[beg + i] = n_claim;
     }
     // per-cloud statistics: warp-aggregated
-    const unsigned m_att = __ballot_sync(0xffffffffu, keep && out_l == 1.0f && ch < LSS_N_CHANNELS);
+    const unsigned m_att = __ballot_sync(0xffffffffu, keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS);
     const unsigned m_rem = __ballot_sync(0xffffffffu, removed);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, s);
@@ -526,15 +528,17 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     const float *d_pts_sorted = s.d_points;
     const float *d_theta = s.d_theta;
     if (!(s.flags & LSS_FLAG_ASSUME_SORTED)) {
-        k_channel_sort<<<B, SORT_TPB, 0, stream>>>(s.d_points, s.d_theta, d_off, d_sorted,
-                                                   s.d_theta ? d_theta_sorted : nullptr, d_perm);
-        e->launches++;
+        {
+            KernelTimer kt(e, LSS_K_SORT, stream);
+            k_channel_sort<<<B, SORT_TPB, 0, stream>>>(s.d_points, s.d_theta, d_off, d_sorted,
+                                                       s.d_theta ? d_theta_sorted : nullptr, d_perm);
+        }
         d_pts_sorted = d_sorted;
         d_theta = s.d_theta ? d_theta_sorted : nullptr;
     } else if (s.d_out_perm) {
         dim3 g((unsigned)((max_n + 255) / 256), B);
+        KernelTimer kt(e, LSS_K_SORT, stream);
         k_identity_perm<<<g, 256, 0, stream>>>(d_off, d_perm);
-        e->launches++;
     }
 
     DevArgs a;
@@ -563,10 +567,18 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.counters = d_counters;
     a.status = e->d_status;
     dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
-    k_snowfall<<<grid, SNOW_TPB, 0, stream>>>(a);
-    k_compact<<<B, SORT_TPB, 0, stream>>>(d_aug, d_keep, d_off, s.d_out_points, s.d_out_counts);
-    k_finalize<<<(B + 127) / 128, 128, 0, stream>>>(s.d_out_stats, d_counters, B);
-    e->launches += 3;
+    {
+        KernelTimer kt(e, LSS_K_SNOWFALL, stream);
+        k_snowfall<<<grid, SNOW_TPB, 0, stream>>>(a);
+    }
+    {
+        KernelTimer kt(e, LSS_K_COMPACT, stream);
+        k_compact<<<B, SORT_TPB, 0, stream>>>(d_aug, d_keep, d_off, s.d_out_points, s.d_out_counts);
+    }
+    {
+        KernelTimer kt(e, LSS_K_FINALIZE, stream);
+        k_finalize<<<(B + 127) / 128, 128, 0, stream>>>(s.d_out_stats, d_counters, B);
+    }
     LSS_CUDA_CHECK(e, cudaGetLastError());
     return LSS_OK;
 }

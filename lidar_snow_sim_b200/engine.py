@@ -176,6 +176,18 @@ class SnowfallEngine:
     def launch_count(self):
         return int(self.lib.lss_launch_count(self.h))
 
+    def set_profiling(self, enable=True):
+        _lib.check(self.lib.lss_set_profiling(self.h, 1 if enable else 0), self.h)
+
+    def kernel_times(self, reset=True):
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        n = 6
+        ms = np.zeros(n, dtype=np.float64)
+        calls = np.zeros(n, dtype=np.int64)
+        _lib.check(self.lib.lss_kernel_times(self.h, 1 if reset else 0, _ptr(ms), _ptr(calls), n), self.h)
+        return {self.lib.lss_kernel_name(k).decode(): (float(ms[k]), int(calls[k])) for k in range(n)}
+
 
 _default_engines = {}
 

@@ -39,3 +39,85 @@ def particle_file_prefix(mode: str, snowfall_rate: float, terminal_velocity: flo
     rain_rate = snowfall_rate_to_rainfall_rate(float(snowfall_rate), float(terminal_velocity))
     occupancy = compute_occupancy(float(snowfall_rate), float(terminal_velocity))
     return f'{mode}_{rain_rate}_{occupancy}'
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# particle tables
+# ----------------------------------------------------------------------------------------------------------------------
+_DIST = {'gunn': 0, 'sekhon': 1}
+
+
+def _pcg_state(rng):
+    st = rng.bit_generator.state
+    if st['bit_generator'] != 'PCG64':
+        raise NotImplementedError('dart_throwing needs a PCG64-backed numpy Generator (np.random.default_rng)')
+    s, inc = st['state']['state'], st['state']['inc']
+    mask = (1 << 64) - 1
+    return st, np.array([s >> 64, s & mask, inc >> 64, inc & mask], dtype=np.uint64)
+
+
+def _expected_capacity(occupancy_ratio, precipitation_rate, R_0, distribution):
+    """Upper bound on the number of accepted disks: total area / mean disk area, with head-room."""
+    rate = gunn_marshall(precipitation_rate) if distribution == 'gunn' else sekhon_srivastava(precipitation_rate)
+    mean_d = 10.0 / rate / 1000.0                    # mean diameter [m]
+    mean_area = np.pi * (2.0 / 3.0) * mean_d ** 2 / 2.0     # E[pi (d^2/4 - h^2)] = pi d^2/6, E[d^2] = 2 mean^2
+    n = occupancy_ratio * np.pi * R_0 ** 2 / max(mean_area, 1e-12)
+    return int(n * 1.5) + 4096
+
+
+def dart_throwing(occupancy_ratio: float, precipitation_rate: float, R_0: float, rng: np.random.Generator,
+                  distribution: str = 'sekhon_srivastava', show_progessbar: bool = False) -> np.ndarray:
+    """
+    Same call as the reference's dart_throwing (sampling.py:90-194): N-by-3 float64 array of disks (x, y, r) [m].
+    Runs in the engine's native sampler and advances `rng` exactly as the reference would have.
+    """
+    import ctypes
+    from .. import _lib
+    if distribution not in _DIST:
+        raise NotImplementedError('Distribution model unknown.')            # sampling.py:113
+    lib = _lib.load()
+    st, words = _pcg_state(rng)
+    cap = _expected_capacity(occupancy_ratio, precipitation_rate, R_0, distribution)
+    while True:
+        w = words.copy()
+        out = np.empty((cap, 3), dtype=np.float64)
+        n = ctypes.c_int64(0)
+        rc = lib.lss_dart_throwing(float(occupancy_ratio), float(precipitation_rate), float(R_0), _DIST[distribution],
+                                   ctypes.c_void_p(w.ctypes.data), ctypes.c_void_p(out.ctypes.data), cap,
+                                   ctypes.byref(n))
+        if rc == _lib.LSS_ERR_WORKSPACE:
+            cap *= 2
+            continue
+        _lib.check(rc)
+        break
+    st['state']['state'] = (int(w[0]) << 64) | int(w[1])
+    rng.bit_generator.state = st
+    return out[:n.value].copy()
+
+
+def sample_table_set(mode: str, snowfall_rate: float, terminal_velocity: float, seed: int = 1000, R_0: float = 80.0,
+                     n_planes: int = 64, n_threads: int = 0):
+    """
+    The 64 planes of one (snowfall_rate, terminal_velocity) configuration (sampling.py:360-413), plane k drawn from
+    np.random.default_rng(seed + k).  Returns a list of (Np_k, 3) float64 arrays.
+    """
+    import ctypes
+    from .. import _lib
+    lib = _lib.load()
+    occ = compute_occupancy(float(snowfall_rate), float(terminal_velocity))
+    rr = float(snowfall_rate_to_rainfall_rate(float(snowfall_rate), float(terminal_velocity)))
+    states = np.stack([_pcg_state(np.random.default_rng(seed + k))[1] for k in range(n_planes)])
+    cap = _expected_capacity(occ, rr, R_0, mode)
+    while True:
+        w = np.ascontiguousarray(states.copy())
+        out = np.empty((n_planes, cap, 3), dtype=np.float64)
+        counts = np.zeros(n_planes, dtype=np.int64)
+        rc = lib.lss_dart_throwing_planes(n_planes, occ, rr, float(R_0), _DIST[mode], ctypes.c_void_p(w.ctypes.data),
+                                          ctypes.c_void_p(out.ctypes.data), cap, ctypes.c_void_p(counts.ctypes.data),
+                                          int(n_threads))
+        if rc == _lib.LSS_ERR_WORKSPACE:
+            cap *= 2
+            continue
+        _lib.check(rc)
+        break
+    return [out[k, :counts[k]].copy() for k in range(n_planes)]
