@@ -41,7 +41,9 @@ typedef enum {
     LSS_ERR_NEGATIVE_INTENSITY = 5,  /* AssertionError analogue (simulation.py:184) */
     LSS_ERR_OCCLUDER_OVERFLOW = 6,   /* more occluders on one beam than the engine's per-beam capacity */
     LSS_ERR_WORKSPACE = 7,        /* caller-supplied workspace too small */
-    LSS_ERR_NO_SENSOR = 8         /* AssertionError analogue: sensor constants missing (simulation.py:35,474-480) */
+    LSS_ERR_NO_SENSOR = 8,        /* AssertionError analogue: sensor constants missing (simulation.py:35,474-480) */
+    LSS_ERR_TOO_FEW_GROUND = 9    /* TypeError analogue: fewer than 3 ground points, estimate_laser_parameters returns
+                                     None (tools/wet_ground/augmentation.py:213-214) and simulation.py:462 fails */
 } lss_status;
 
 /* flags for lss_snowfall_batch */
@@ -130,6 +132,19 @@ LSS_API int64_t lss_snowfall_workspace_bytes(int64_t n_total, int n_clouds);
 LSS_API lss_status lss_check_async(lss_engine *e, void *stream);
 /* number of kernel launches the engine has enqueued since creation (bench.py's gpu_launches) */
 LSS_API int64_t lss_launch_count(const lss_engine *e);
+/* ---- per-cloud pre-pass ----------------------------------------------------------------------------------------------
+ * Ground plane (calculate_plane, tools/wet_ground/planes.py:12-50), ground mask + incident angle
+ * (simulation.py:450-455), estimate_laser_parameters (tools/wet_ground/augmentation.py:195-266, 'linear') and the
+ * degree-2 noise-threshold polynomial (simulation.py:462-467) for every cloud of a batch.  lss_snowfall_batch runs
+ * the same code with LSS_FLAG_DEVICE_PREPASS; this entry point exposes the results.
+ *   h_plane_in   float64[n_clouds*4] (w0, w1, w2, h) or NULL.  NULL: estimated on the device (deterministic RANSAC).
+ *   d_poly_out   float64[n_clouds*3]  np.polyfit order (highest power first), device
+ *   d_plane_out  float64[n_clouds*4] or NULL, device                                                                   */
+LSS_API lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets,
+                                    int n_clouds, double noise_floor, const double *h_plane_in, double *d_poly_out,
+                                    double *d_plane_out, void *d_workspace, int64_t workspace_bytes, void *stream);
+LSS_API int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds);
+
 /* ---- snowflake table sampler ---------------------------------------------------------------------------------------
  * dart_throwing(occupancy_ratio, precipitation_rate, R_0, rng, distribution) of tools/snowfall/sampling.py:90-194:
  * sequential rejection sampling of non-overlapping disks in a disk of radius R_0 until the occupied area reaches

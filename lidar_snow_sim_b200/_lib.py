@@ -19,6 +19,7 @@ LSS_ERR_NEGATIVE_INTENSITY = 5
 LSS_ERR_OCCLUDER_OVERFLOW = 6
 LSS_ERR_WORKSPACE = 7
 LSS_ERR_NO_SENSOR = 8
+LSS_ERR_TOO_FEW_GROUND = 9
 
 FLAG_THRESHOLD_FILTER = 0x1
 FLAG_CAMERA_FOV = 0x2
@@ -35,6 +36,7 @@ _EXC = {
     LSS_ERR_OCCLUDER_OVERFLOW: RuntimeError,
     LSS_ERR_WORKSPACE: RuntimeError,
     LSS_ERR_NO_SENSOR: AssertionError,           # simulation.py:35
+    LSS_ERR_TOO_FEW_GROUND: TypeError,           # estimate_laser_parameters -> None, simulation.py:457-462
 }
 
 # every symbol include/lidar_snow_sim.h declares: (name, restype, argtypes)
@@ -60,6 +62,8 @@ SIGNATURES = [
     ('lss_check_async', _c.c_int, [_P, _P]),
     ('lss_launch_count', _c.c_int64, [_P]),
     ('lss_debug_range_grid', _c.c_int, [_P]),
+    ('lss_noise_threshold_poly', _c.c_int, [_P, _P, _P, _c.c_int, _c.c_double, _P, _P, _P, _P, _c.c_int64, _P]),
+    ('lss_prepass_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
     ('lss_dart_throwing', _c.c_int, [_c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P, _c.c_int64,
                                      _c.POINTER(_c.c_int64)]),
     ('lss_dart_throwing_planes', _c.c_int, [_c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P,

@@ -41,6 +41,7 @@ const char *lss_status_string(lss_status s)
         case LSS_ERR_OCCLUDER_OVERFLOW: return "too many occluders on one beam";
         case LSS_ERR_WORKSPACE: return "workspace too small";
         case LSS_ERR_NO_SENSOR: return "sensor / camera constants not set";
+        case LSS_ERR_TOO_FEW_GROUND: return "fewer than 3 ground points: laser parameters cannot be estimated";
     }
     return "unknown status";
 }
@@ -244,6 +245,31 @@ lss_status lss_snowfall_batch(lss_engine *e, int table_id, const float *d_points
     a.d_workspace = d_workspace;
     a.workspace_bytes = workspace_bytes;
     return lss_snowfall_run(e, a, (cudaStream_t)stream);
+}
+
+int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds)
+{
+    if (n_total < 0 || n_clouds < 0) return -1;
+    return lss_prepass_ws_bytes(n_total, n_clouds) + 256 + (int64_t)(n_clouds + 1) * 8;
+}
+
+lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets, int n_clouds,
+                                    double noise_floor, const double *h_plane_in, double *d_poly_out,
+                                    double *d_plane_out, void *d_workspace, int64_t workspace_bytes, void *stream)
+{
+    if (!e) return LSS_ERR_INVALID_ARG;
+    if (!d_points || !h_cloud_offsets || n_clouds <= 0 || !d_poly_out || !d_workspace)
+        return lss_fail(e, LSS_ERR_INVALID_ARG, "null argument");
+    if (h_cloud_offsets[0] != 0) return lss_fail(e, LSS_ERR_INVALID_ARG, "cloud_offsets[0] must be 0");
+    DeviceGuard g(e->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t off_bytes = ((int64_t)(n_clouds + 1) * 8 + 255) / 256 * 256;
+    if (workspace_bytes < off_bytes + lss_prepass_ws_bytes(h_cloud_offsets[n_clouds], n_clouds))
+        return lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small");
+    int64_t *d_off = (int64_t *)d_workspace;
+    LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, h_cloud_offsets, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
+    return lss_prepass_run(e, d_points, d_off, h_cloud_offsets, n_clouds, 0.5, noise_floor, 0, h_plane_in, d_poly_out,
+                           d_plane_out, (char *)d_workspace + off_bytes, workspace_bytes - off_bytes, nullptr, st);
 }
 
 lss_status lss_check_async(lss_engine *e, void *stream)

@@ -138,4 +138,10 @@ struct SnowfallArgs {
     int64_t workspace_bytes;
 };
 lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &a, cudaStream_t stream);
+// implemented in prepass.cu
+int64_t lss_prepass_ws_bytes(int64_t n_total, int n_clouds);
+lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int64_t *h_cloud_off,
+                           int n_clouds, double delta, double noise_floor, int flat_earth, const double *h_plane_in,
+                           double *d_poly_out, double *d_plane_out, void *d_ws, int64_t ws_bytes, void **cloudpre_out,
+                           cudaStream_t stream);
 int64_t lss_snowfall_ws_bytes(int64_t n_total, int n_clouds);

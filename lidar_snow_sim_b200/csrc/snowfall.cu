@@ -233,49 +233,56 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
 
         if (L > 0 && !overflow) {
             // ---- compute_occlusion_dict (simulation.py:231-295) ---------------------------------------------------
+            // The reference splits the beam into elementary sub-intervals between all sorted end points and lets the
+            // particles claim, nearest first, every still-unclaimed piece inside their own interval.  Equivalent
+            // formulation used here: keep the union of the intervals claimed so far as a list of disjoint, non-touching
+            // intervals; a particle claims |[a1,a2]| - |[a1,a2] n union| and is dropped iff [a1,a2] is contained in
+            // one union interval (or a1 >= a2, the reference's empty range(i1, i2)).  The hard target gets what is left
+            // between the smallest and the largest end point -- including the ~2 pi gap of the seam quirk.
             double rb = right;
             if (straddle) {
                 rb = right - LSS_TWO_PI;
                 for (int j = 0; j < L; j++) if (ha1[j] > ha2[j]) ha1[j] -= LSS_TWO_PI;
             }
-            double ep[2 * LSS_MAX_OCC + 2];
-            int ne = 0;
-            {   // sorted(set(endpoints)): insertion with de-duplication
-                auto put = [&](double v) {
-                    int k = ne - 1;
-                    while (k >= 0 && ep[k] > v) k--;
-                    if (k >= 0 && ep[k] == v) return;
-                    for (int q = ne - 1; q > k; q--) ep[q + 1] = ep[q];
-                    ep[k + 1] = v;
-                    ne++;
-                };
-                put(rb);
-                for (int j = 0; j < L; j++) { put(ha1[j]); put(ha2[j]); }
-                put(left);
-            }
-            signed char owner[2 * LSS_MAX_OCC + 2];
-            for (int k = 0; k < ne - 1; k++) owner[k] = -1;
+            double ulo[LSS_MAX_OCC], uhi[LSS_MAX_OCC];
+            int nu = 0;
+            double ep_min = fmin(rb, left), ep_max = fmax(rb, left), claimed_total = 0.0;
             int P = 0;          // pulses: claiming particles in range order, then the hard target
             for (int j = 0; j < L; j++) {
-                int i1 = -1, i2 = -1;
-                for (int k = 0; k < ne; k++) { if (ep[k] == ha1[j]) i1 = k; if (ep[k] == ha2[j]) i2 = k; }
-                bool made = false;
-                double s = 0.0;
-                for (int k = i1; k < i2; k++) {
-                    if (owner[k] < 0) { owner[k] = (signed char)j; made = true; s += ep[k + 1] - ep[k]; }
+                const double lo = ha1[j], hi = ha2[j];
+                ep_min = fmin(ep_min, fmin(lo, hi));
+                ep_max = fmax(ep_max, fmax(lo, hi));
+                if (!(lo < hi)) continue;
+                bool contained = false;
+                double cov = 0.0;
+                for (int u = 0; u < nu; u++) {
+                    contained |= (ulo[u] <= lo) && (hi <= uhi[u]);
+                    const double ov = fmin(hi, uhi[u]) - fmax(lo, ulo[u]);
+                    if (ov > 0.0) cov += ov;
                 }
-                if (made) {
-                    double ratio = s / a.div_rad;
-                    ratio = ratio < 0 ? 0 : (ratio > 1 ? 1 : ratio);
-                    hr[P] = hr[j];          // P <= j: safe in place
-                    ha1[P] = ratio;
-                    P++;
+                if (contained) continue;
+                const double claimed = (hi - lo) - cov;
+                claimed_total += claimed;
+                double nlo = lo, nhi = hi;      // merge [lo, hi] into the union (absorb overlapping / touching pieces)
+                int w = 0;
+                for (int u = 0; u < nu; u++) {
+                    if (ulo[u] <= nhi && uhi[u] >= nlo && ulo[u] <= hi && uhi[u] >= lo) {
+                        nlo = fmin(nlo, ulo[u]);
+                        nhi = fmax(nhi, uhi[u]);
+                    } else {
+                        ulo[w] = ulo[u]; uhi[w] = uhi[u]; w++;
+                    }
                 }
+                ulo[w] = nlo; uhi[w] = nhi;
+                nu = w + 1;
+                double ratio = claimed / a.div_rad;
+                ratio = ratio < 0 ? 0 : (ratio > 1 ? 1 : ratio);
+                hr[P] = hr[j];          // P <= j: safe in place
+                ha1[P] = ratio;
+                P++;
             }
             n_claim = P;
-            double s_un = 0.0;
-            for (int k = 0; k < ne - 1; k++) if (owner[k] < 0) s_un += ep[k + 1] - ep[k];
-            double ratio_hard = s_un / a.div_rad;
+            double ratio_hard = ((ep_max - ep_min) - claimed_total) / a.div_rad;
             ratio_hard = ratio_hard < 0 ? 0 : (ratio_hard > 1 ? 1 : ratio_hard);
 
             if (P > 0) {
@@ -306,23 +313,39 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                 if (bad) {
                     raise_status(a.status, LSS_ERR_RANGE_INDEX);
                 } else {
+                    // argmax of the summed waveform.  Only bins inside some pulse window are non-zero.  Windows are
+                    // visited in ascending range; pulses whose windows overlap form a group whose bins are summed in
+                    // full (in dict order, like the reference's i[k] +=); an isolated pulse A sin^2(pi (R - r)/(c tau))
+                    // is unimodal and symmetric about r + c tau / 2, so its maximum over the grid is at one of the
+                    // three samples around the sample nearest to the peak.
                     double best = 0.0;
                     int kbest = 0;
-                    for (int j = 0; j <= P; j++) {
-                        for (int k = ks[j]; k < ke[j]; k++) {
-                            bool seen = false;
-                            for (int q = 0; q < j; q++) seen |= (k >= ks[q] && k < ke[q]);
-                            if (seen) continue;
+                    const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
+                    int j = 0;
+                    while (j <= P) {
+                        int g1 = j, k_lo = ks[j], k_hi = ke[j];
+                        while (g1 + 1 <= P && ks[g1 + 1] < k_hi) {
+                            g1++;
+                            k_lo = min(k_lo, ks[g1]);
+                            k_hi = max(k_hi, ke[g1]);
+                        }
+                        if (g1 == j) {
+                            const int k0 = (int)rint((rj[j] + ctau / 2) * inv_step);
+                            k_lo = max(k_lo, k0 - 1);
+                            k_hi = min(k_hi, k0 + 2);
+                        }
+                        for (int k = k_lo; k < k_hi; k++) {
                             const double Rk = __ldg(&a.R[k]);
                             double v = 0.0;
-                            for (int q = 0; q <= P; q++) {
+                            for (int q = j; q <= g1; q++) {
                                 if (k >= ks[q] && k < ke[q]) {
                                     const double sn = sin((LSS_PI * (Rk - rj[q])) / ctau);
                                     v += amp[q] * (sn * sn);
                                 }
                             }
-                            if (v > best || (v == best && v > 0.0 && k < kbest)) { best = v; kbest = k; }
+                            if (v > best) { best = v; kbest = k; }      // ascending k: first maximum wins (np.argmax)
                         }
+                        j = g1 + 1;
                     }
                     const double d_max = ((double)kbest / 10) - (ctau / 2);
                     const double q1 = 1 - d_max / 120;
@@ -448,7 +471,7 @@ __global__ void k_finalize(double *stats, const int *counters, int n_clouds)
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    int64_t sorted, theta, keep, perm, aug, cloud_off, order, thresh, counters, total;
+    int64_t sorted, theta, keep, perm, aug, cloud_off, order, thresh, counters, prepass, prepass_bytes, total;
 };
 
 WsLayout ws_layout(int64_t n_total, int n_clouds)
@@ -464,6 +487,8 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     w.order = o;     o = align_up(o + (int64_t)n_clouds * LSS_N_CHANNELS * 4, 256);
     w.thresh = o;    o = align_up(o + (int64_t)n_clouds * 3 * 8, 256);
     w.counters = o;  o = align_up(o + (int64_t)n_clouds * 2 * 4, 256);
+    w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
+    w.prepass = o;   o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
     return w;
 }
@@ -495,8 +520,6 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     if (s.workspace_bytes < w.total || !s.d_workspace) return lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small");
     if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && !s.h_thresh_poly && !(s.flags & LSS_FLAG_DEVICE_PREPASS))
         return lss_fail(e, LSS_ERR_INVALID_ARG, "threshold filter needs h_thresh_poly or LSS_FLAG_DEVICE_PREPASS");
-    if (s.flags & LSS_FLAG_DEVICE_PREPASS)
-        return lss_fail(e, LSS_ERR_INVALID_ARG, "device pre-pass not available in this build");
     if ((s.flags & LSS_FLAG_CAMERA_FOV) && !e->has_camera)
         return lss_fail(e, LSS_ERR_NO_SENSOR, "camera calibration not set");
     const double div_rad = s.beam_divergence_deg * (LSS_PI / 180.0);
@@ -539,6 +562,13 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         dim3 g((unsigned)((max_n + 255) / 256), B);
         KernelTimer kt(e, LSS_K_SORT, stream);
         k_identity_perm<<<g, 256, 0, stream>>>(d_off, d_perm);
+    }
+
+    if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly) {
+        // plane + laser parameters + threshold polynomial from the channel-sorted cloud (simulation.py:449-467)
+        lss_status ps = lss_prepass_run(e, d_pts_sorted, d_off, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, nullptr,
+                                        d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, stream);
+        if (ps != LSS_OK) return ps;
     }
 
     DevArgs a;

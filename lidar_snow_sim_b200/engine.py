@@ -168,6 +168,25 @@ class SnowfallEngine:
         _lib.check(st, self.h)
         return out
 
+    def noise_threshold_poly(self, points, cloud_offsets, noise_floor=0.7, plane=None):
+        """Device pre-pass only: returns (poly (B,3) float64 tensor in np.polyfit order, plane (B,4) tensor).
+        plane: optional host array (B,4) = (w0, w1, w2, h) to use instead of the RANSAC estimate."""
+        off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
+        B = off.shape[0] - 1
+        N = int(off[-1])
+        assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.shape == (N, 5)
+        pl = None if plane is None else np.ascontiguousarray(plane, dtype=np.float64).reshape(B, 4)
+        with torch.cuda.device(self.device):
+            need = self.lib.lss_prepass_workspace_bytes(N, B)
+            ws = torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device)
+            poly = torch.empty((B, 3), dtype=torch.float64, device=self.device)
+            plane_out = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+            st = self.lib.lss_noise_threshold_poly(self.h, _ptr(points), _ptr(off), B, float(noise_floor), _ptr(pl),
+                                                   _ptr(poly), _ptr(plane_out), _ptr(ws), int(ws.numel()),
+                                                   self._stream())
+        _lib.check(st, self.h)
+        return poly, plane_out
+
     def check(self):
         """Synchronise the current stream and raise the exception type the reference would have raised."""
         with torch.cuda.device(self.device):

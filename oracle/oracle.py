@@ -258,7 +258,7 @@ def calculate_plane(pointcloud, standart_height=-1.55):
 
 
 def estimate_laser_parameters(pointcloud_planes, calculated_indicent_angle, power_factor=15, noise_floor=0.7,
-                              estimation_method='linear'):
+                              estimation_method='linear', least_populated='argpartition'):
     """tools/wet_ground/augmentation.py:195-266, 'linear' branch, with the idx1[0] shim (NumPy >= 1.23)."""
     from scipy.stats import linregress
     normalized_intensitites = pointcloud_planes[:, 3] / np.cos(calculated_indicent_angle)
@@ -275,7 +275,13 @@ def estimate_laser_parameters(pointcloud_planes, calculated_indicent_angle, powe
                                           range=((10, 70), (5, np.abs(np.max(normalized_intensitites)))))
     idx = np.where(hist == 0)
     hist[idx] = len(pointcloud_planes)
-    ymins = np.argpartition(hist, 2, axis=1)[:, 0]
+    if least_populated == 'argpartition':
+        # implementation-defined: one of the three least populated bins.  NumPy's portable introselect (kth < 3 ->
+        # `dumb_select`, the only path in the NumPy 1.2x the reference was written against) returns the FIRST minimum;
+        # AVX-512 builds of NumPy >= 1.25 (x86-simd-sort argselect) return a different one of the three.
+        ymins = np.argpartition(hist, 2, axis=1)[:, 0]
+    else:
+        ymins = np.argmin(hist, axis=1)           # 'first_min': the portable introselect result
     min_vals = yedges[ymins]
     idx = np.where(min_vals > 5)
     min_vals = min_vals[idx]
@@ -289,7 +295,7 @@ def estimate_laser_parameters(pointcloud_planes, calculated_indicent_angle, powe
     return relative_output_intensity, adaptive_noise_threshold, p, stat_values
 
 
-def noise_threshold_poly(pc, w, h, noise_floor=0.7):
+def noise_threshold_poly(pc, w, h, noise_floor=0.7, least_populated='argpartition'):
     """simulation.py:450-467: degree-2 polynomial of the adaptive noise threshold over range."""
     ground = np.logical_and(np.matmul(pc[:, :3], np.asarray(w)) + h < 0.5,
                             np.matmul(pc[:, :3], np.asarray(w)) + h > -0.5)
@@ -297,7 +303,8 @@ def noise_threshold_poly(pc, w, h, noise_floor=0.7):
     calculated_indicent_angle = np.arccos(np.divide(np.matmul(pc_ground[:, :3], np.asarray(w)),
                                                     np.linalg.norm(pc_ground[:, :3], axis=1) * np.linalg.norm(w)))
     _, adaptive_noise_threshold, _, _ = estimate_laser_parameters(pc_ground, calculated_indicent_angle,
-                                                                  noise_floor=noise_floor)
+                                                                  noise_floor=noise_floor,
+                                                                  least_populated=least_populated)
     adaptive_noise_threshold *= np.cos(calculated_indicent_angle)
     ground_distances = np.linalg.norm(pc_ground[:, :3], axis=1)
     return np.polyfit(ground_distances, adaptive_noise_threshold, 2)
@@ -320,7 +327,7 @@ def fov_flag(points_xyz, calib):
 
 def augment(pc, tables, beam_divergence, sensor, shuffle=True, only_camera_fov=False, noise_floor=0.7,
             order=None, plane=None, thresh_poly=None, theta_sorted=None, calib=None, threads=None, stable_sort=False,
-            return_internals=False):
+            return_internals=False, least_populated='argpartition'):
     """
     augment() of simulation.py:427-544 with the particle files replaced by in-memory `tables`.
     `order`, `plane`=(w,h), `thresh_poly`, `theta_sorted` let a test inject the values a reference run used
@@ -330,7 +337,7 @@ def augment(pc, tables, beam_divergence, sensor, shuffle=True, only_camera_fov=F
     pc = pc[idx]
     if thresh_poly is None:
         w, h = calculate_plane(pc) if plane is None else plane
-        p = noise_threshold_poly(pc, w, h, noise_floor)
+        p = noise_threshold_poly(pc, w, h, noise_floor, least_populated=least_populated)
     else:
         w, h = plane if plane is not None else (None, None)
         p = np.asarray(thresh_poly, dtype=np.float64)
