@@ -145,6 +145,28 @@ LSS_API lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points
                                     double *d_plane_out, void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds);
 
+/* ---- wet-ground augmentation ------------------------------------------------------------------------------------------
+ * Batched ground_water_augmentation() (tools/wet_ground/augmentation.py:25-161, estimation_method='linear') with the
+ * Fresnel chain of tools/wet_ground/phy_equations.py:35-108, on device-resident clouds.
+ *   d_points          float32[n_total*5]; cloud b starts at row h_cloud_offsets[b]
+ *   d_cloud_counts    int32[n_clouds] device or NULL: valid rows per cloud when the input is the slot-compacted output of
+ *                     lss_snowfall_batch (fused snow -> wet path); NULL: h_cloud_offsets[b+1] - h_cloud_offsets[b]
+ *   water_height, pavement_depth, noise_floor, power_factor, flat_earth, delta, replace: as in the reference signature
+ *   h_plane_in        float64[n_clouds*4] (w0, w1, w2, h) or NULL (device RANSAC, planes.py:12-50)
+ *   d_out_points      float32[n_total*5]: per cloud, non-ground rows first, then the kept ground rows (:150-159),
+ *                     compacted to the front of the cloud's slot
+ *   d_out_intensity64 float64[n_total] or NULL: column 3 of the output rows in the reference's float64
+ *   d_out_counts      int32[n_clouds]
+ *   d_out_passthrough int32[n_clouds] or NULL: 1 where the cloud had < 1000 ground points and is returned unchanged (:51-52)
+ *   d_out_plane       float64[n_clouds*4] or NULL                                                                       */
+LSS_API lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets,
+                                const int32_t *d_cloud_counts, int n_clouds, double water_height, double pavement_depth,
+                                double noise_floor, double power_factor, int flat_earth, double delta, int replace,
+                                const double *h_plane_in, float *d_out_points, double *d_out_intensity64,
+                                int32_t *d_out_counts, int32_t *d_out_passthrough, double *d_out_plane,
+                                void *d_workspace, int64_t workspace_bytes, void *stream);
+LSS_API int64_t lss_wet_ground_workspace_bytes(int64_t n_total, int n_clouds);
+
 /* ---- snowflake table sampler ---------------------------------------------------------------------------------------
  * dart_throwing(occupancy_ratio, precipitation_rate, R_0, rng, distribution) of tools/snowfall/sampling.py:90-194:
  * sequential rejection sampling of non-overlapping disks in a disk of radius R_0 until the occupied area reaches

@@ -268,7 +268,7 @@ lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const 
         return lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small");
     int64_t *d_off = (int64_t *)d_workspace;
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, h_cloud_offsets, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
-    return lss_prepass_run(e, d_points, d_off, h_cloud_offsets, n_clouds, 0.5, noise_floor, 0, h_plane_in, d_poly_out,
+    return lss_prepass_run(e, d_points, d_off, nullptr, h_cloud_offsets, n_clouds, 0.5, noise_floor, 0, 0, 1, h_plane_in, d_poly_out,
                            d_plane_out, (char *)d_workspace + off_bytes, workspace_bytes - off_bytes, nullptr, st);
 }
 

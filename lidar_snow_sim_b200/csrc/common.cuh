@@ -139,9 +139,28 @@ struct SnowfallArgs {
 };
 lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &a, cudaStream_t stream);
 // implemented in prepass.cu
+struct CloudPre {            // per-cloud scratch / results, float64
+    double w[3], h;          // plane
+    double nw;               // |w|
+    int n_window;            // points in the mounting window
+    int n_ground;
+    double ymax;             // |max(I / cos)|           (histogram range, augmentation.py:233)
+    double lin[2];           // first regression  I/cos ~ lin0 * d + lin1       (augmentation.py:216-219)
+    double pmin[2];          // second regression over the per-range-bin minima (augmentation.py:249)
+    double poly[3];          // np.polyfit(d, noise*cos, 2): highest power first  (simulation.py:467)
+    float z_med, mad;
+    int best_trial;
+    int flat;                // flat-earth fallback taken
+};
+// p . w exactly as written, without FMA contraction, so that every kernel classifies a point identically
+__device__ __forceinline__ double lss_plane_dot(double x, double y, double z, const double *w)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(x, w[0]), __dmul_rn(y, w[1])), __dmul_rn(z, w[2]));
+}
 int64_t lss_prepass_ws_bytes(int64_t n_total, int n_clouds);
-lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int64_t *h_cloud_off,
-                           int n_clouds, double delta, double noise_floor, int flat_earth, const double *h_plane_in,
+lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int32_t *d_cloud_cnt,
+                           const int64_t *h_cloud_off, int n_clouds, double delta, double noise_floor, int flat_earth,
+                           int range64, int raise_few_ground, const double *h_plane_in,
                            double *d_poly_out, double *d_plane_out, void *d_ws, int64_t ws_bytes, void **cloudpre_out,
                            cudaStream_t stream);
 int64_t lss_snowfall_ws_bytes(int64_t n_total, int n_clouds);

@@ -25,23 +25,13 @@ constexpr int PP_TPB = 256;
 constexpr int HIST_NX = 50, HIST_NY = 2555;      // augmentation.py:232
 constexpr int RANSAC_T = 128;
 
-struct CloudPre {            // per-cloud scratch / results, float64
-    double w[3], h;          // plane
-    double nw;               // |w|
-    int n_window;            // points in the mounting window
-    int n_ground;
-    double ymax;             // |max(I / cos)|           (histogram range, augmentation.py:233)
-    double lin[2];           // first regression  I/cos ~ lin0 * d + lin1       (augmentation.py:216-219)
-    double pmin[2];          // second regression over the per-range-bin minima (augmentation.py:249)
-    double poly[3];          // np.polyfit(d, noise*cos, 2): highest power first  (simulation.py:467)
-    float z_med, mad;
-    int best_trial;
-    int flat;                // flat-earth fallback taken
-};
 
 struct PreArgs {
     const float *pts;
-    const int64_t *cloud_off;
+    const int64_t *cloud_off;  // [B+1]: cloud b starts at row cloud_off[b]
+    const int32_t *cloud_cnt;  // optional [B]: number of valid rows of cloud b (slot-compacted input); null: off[b+1]-off[b]
+    int raise_few;             // latch LSS_ERR_TOO_FEW_GROUND when a cloud has < 3 ground points (snowfall path)
+    int range64;               // ranges in float64 (wet ground: the reference's ground array is float64) or float32
     int n_clouds;
     double delta;            // ground band half width: 0.5 in simulation.py:450, `delta` in augmentation.py:46
     double noise_floor;
@@ -99,7 +89,7 @@ __global__ void __launch_bounds__(1024) k_window(PreArgs a)
     __shared__ int run_s;
     const int b = blockIdx.x;
     const int64_t beg = a.cloud_off[b];
-    const int n = (int)(a.cloud_off[b + 1] - beg);
+    const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) run_s = 0;
     __syncthreads();
@@ -340,11 +330,10 @@ __device__ __forceinline__ GroundPt ground_point(const PreArgs &a, const CloudPr
 {
     GroundPt g;
     const double x = r[0], y = r[1], z = r[2];
-    const double pw = x * cp.w[0] + y * cp.w[1] + z * cp.w[2];            // np.matmul(pc[:, :3], w)
+    const double pw = lss_plane_dot(x, y, z, cp.w);                        // np.matmul(pc[:, :3], w)
     const double hgt = pw + cp.h;
     g.ground = (hgt < a.delta) && (hgt > -a.delta);                       // simulation.py:450-451
-    const float d32 = range32(r[0], r[1], r[2]);
-    g.d = (double)d32;
+    g.d = a.range64 ? sqrt((x * x + y * y) + z * z) : (double)range32(r[0], r[1], r[2]);
     double c;
     if (a.flat_earth) c = -(z) / (g.d * 1.0);                             // augmentation.py:61-63
     else c = pw / (g.d * cp.nw);                                          // simulation.py:454-455
@@ -362,7 +351,7 @@ __global__ void __launch_bounds__(PP_TPB) k_ground_stats(PreArgs a)
     const int b = blockIdx.y;
     const CloudPre cp = a.cp[b];
     const int64_t beg = a.cloud_off[b];
-    const int n = (int)(a.cloud_off[b + 1] - beg);
+    const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
     double v[6] = {0, 0, 0, 0, 0, 0};
     double vmax = -1e300;
     for (int i = blockIdx.x * PP_TPB + threadIdx.x; i < n; i += gridDim.x * PP_TPB) {
@@ -405,7 +394,7 @@ __global__ void k_ground_stats_final(PreArgs a, int n_blocks)
         cp.lin[1] = (my_ + 50.0) - slope * (mx_ + 30.0);
     } else {
         cp.lin[0] = cp.lin[1] = 0.0;
-        atomicMax(a.status, LSS_ERR_TOO_FEW_GROUND);
+        if (a.raise_few) atomicMax(a.status, LSS_ERR_TOO_FEW_GROUND);
     }
 }
 
@@ -430,7 +419,7 @@ __global__ void __launch_bounds__(PP_TPB) k_ground_hist(PreArgs a)
     const CloudPre cp = a.cp[b];
     if (cp.n_ground < 3) return;
     const int64_t beg = a.cloud_off[b];
-    const int n = (int)(a.cloud_off[b + 1] - beg);
+    const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
     unsigned *hist = a.hist + (size_t)b * HIST_NX * HIST_NY;
     for (int i = blockIdx.x * PP_TPB + threadIdx.x; i < n; i += gridDim.x * PP_TPB) {
         const GroundPt g = ground_point(a, cp, a.pts + (beg + i) * 5);
@@ -500,7 +489,7 @@ __global__ void __launch_bounds__(PP_TPB) k_poly_sums(PreArgs a)
     const int b = blockIdx.y;
     const CloudPre cp = a.cp[b];
     const int64_t beg = a.cloud_off[b];
-    const int n = (int)(a.cloud_off[b + 1] - beg);
+    const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cp.n_ground >= 3) {
         for (int i = blockIdx.x * PP_TPB + threadIdx.x; i < n; i += gridDim.x * PP_TPB) {
@@ -583,8 +572,9 @@ int64_t lss_prepass_ws_bytes(int64_t n_total, int n_clouds) { return prepass_lay
 // Runs the whole pre-pass for a batch.  d_poly_out / d_plane_out: device [B*3] / [B*4] (either may be null).
 // h_plane_in: optional host [B*4] (w0, w1, w2, h) to use instead of the RANSAC estimate.
 // d_cloudpre_out: optional device pointer receiving the address of the per-cloud CloudPre records (for wet ground).
-lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int64_t *h_cloud_off,
-                           int n_clouds, double delta, double noise_floor, int flat_earth, const double *h_plane_in,
+lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int32_t *d_cloud_cnt,
+                           const int64_t *h_cloud_off, int n_clouds, double delta, double noise_floor, int flat_earth,
+                           int range64, int raise_few_ground, const double *h_plane_in,
                            double *d_poly_out, double *d_plane_out, void *d_ws, int64_t ws_bytes, void **cloudpre_out,
                            cudaStream_t stream)
 {
@@ -596,6 +586,9 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
     PreArgs a;
     a.pts = d_pts;
     a.cloud_off = d_cloud_off;
+    a.cloud_cnt = d_cloud_cnt;
+    a.range64 = range64;
+    a.raise_few = raise_few_ground;
     a.n_clouds = B;
     a.delta = delta;
     a.noise_floor = noise_floor;

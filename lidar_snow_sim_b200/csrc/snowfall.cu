@@ -178,6 +178,12 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
     double diff = 0.0;
     int n_claim = 0;
     const int ch = channel_bin(pch);
+    const double ctau = 299792458.0 * 1e-8;
+
+    // per-beam lists (local memory): hits (a1, a2, range) -> after claiming: pulses (amplitude, range, window)
+    double ha1[LSS_MAX_OCC + 1], ha2[LSS_MAX_OCC], hr[LSS_MAX_OCC + 1];
+    int ks[LSS_MAX_OCC + 1], ke[LSS_MAX_OCC + 1];
+    int n_pulses = 0;            // > 0: this beam has a waveform to solve (claiming particles + hard target)
 
     if (active && ch < LSS_N_CHANNELS) {
         out_l = 0.0f;
@@ -193,7 +199,6 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
         const bool straddle = right > left;
 
         // ---- candidate scan: one azimuth bucket of this channel's plane -------------------------------------------
-        double ha1[LSS_MAX_OCC], ha2[LSS_MAX_OCC], hr[LSS_MAX_OCC];
         int L = 0;
         bool overflow = false;
         const int plane = a.order[b * LSS_N_CHANNELS + ch];
@@ -286,14 +291,10 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
             ratio_hard = ratio_hard < 0 ? 0 : (ratio_hard > 1 ? 1 : ratio_hard);
 
             if (P > 0) {
-                // ---- waveform (simulation.py:118-156) -------------------------------------------------------------
-                const double ctau = 299792458.0 * 1e-8;
+                // ---- pulses of the waveform (simulation.py:137-149) -------------------------------------------------
                 const double beta_0 = 1 * 1e-06 / LSS_PI;
-                const double max_i = a.sensor->max_intensity[ch];
-                const double min_i = a.sensor->min_intensity[ch];
-                const double i_orig = 0.9 * max_i;
+                const double i_orig = 0.9 * a.sensor->max_intensity[ch];
                 const double A = (i_orig / beta_0) * beta_0;        // CA_P0 * beta_0 (quirk: every pulse uses it)
-                int ks[LSS_MAX_OCC + 1], ke[LSS_MAX_OCC + 1];
                 double *amp = ha1, *rj = hr;                         // reuse the hit arrays
                 bool bad = false;
                 for (int j = 0; j < P; j++) {
@@ -310,65 +311,115 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                     amp[P] = (A * ratio_hard * xsi32(d32)) / (double)__fmul_rn(d32, d32);
                     bad |= (ke[P] > LSS_M_EXT) || (ks[P] < 0);
                 }
-                if (bad) {
-                    raise_status(a.status, LSS_ERR_RANGE_INDEX);
-                } else {
-                    // argmax of the summed waveform.  Only bins inside some pulse window are non-zero.  Windows are
-                    // visited in ascending range; pulses whose windows overlap form a group whose bins are summed in
-                    // full (in dict order, like the reference's i[k] +=); an isolated pulse A sin^2(pi (R - r)/(c tau))
-                    // is unimodal and symmetric about r + c tau / 2, so its maximum over the grid is at one of the
-                    // three samples around the sample nearest to the peak.
-                    double best = 0.0;
-                    int kbest = 0;
-                    const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
-                    int j = 0;
-                    while (j <= P) {
-                        int g1 = j, k_lo = ks[j], k_hi = ke[j];
-                        while (g1 + 1 <= P && ks[g1 + 1] < k_hi) {
-                            g1++;
-                            k_lo = min(k_lo, ks[g1]);
-                            k_hi = max(k_hi, ke[g1]);
-                        }
-                        if (g1 == j) {
-                            const int k0 = (int)rint((rj[j] + ctau / 2) * inv_step);
-                            k_lo = max(k_lo, k0 - 1);
-                            k_hi = min(k_hi, k0 + 2);
-                        }
-                        for (int k = k_lo; k < k_hi; k++) {
-                            const double Rk = __ldg(&a.R[k]);
-                            double v = 0.0;
-                            for (int q = j; q <= g1; q++) {
-                                if (k >= ks[q] && k < ke[q]) {
-                                    const double sn = sin((LSS_PI * (Rk - rj[q])) / ctau);
-                                    v += amp[q] * (sn * sn);
-                                }
-                            }
-                            if (v > best) { best = v; kbest = k; }      // ascending k: first maximum wins (np.argmax)
-                        }
-                        j = g1 + 1;
-                    }
-                    const double d_max = ((double)kbest / 10) - (ctau / 2);
-                    const double q1 = 1 - d_max / 120;
-                    double i_max = best + max_i * a.sensor->focal_slope[ch] * fabs(a.sensor->focal_offset[ch] - q1 * q1);
-                    i_max = i_max < min_i ? min_i : (i_max > max_i ? max_i : i_max);
-                    const long long new_i = (long long)i_max;       // int(): truncation
-                    if (fabs(d_max - d) < 2 * (1.0 / 10)) {
-                        out_l = 1.0f;
-                        diff = i_orig - (double)new_i;
-                    } else {
-                        out_l = 2.0f;
-                        const double sc = d_max / d;
-                        out_x = (float)((double)px * sc);
-                        out_y = (float)((double)py * sc);
-                        out_z = (float)((double)pz * sc);
-                    }
-                    if (new_i < 0) raise_status(a.status, LSS_ERR_NEGATIVE_INTENSITY);
-                    double ci = (double)new_i;
-                    ci = ci < min_i ? min_i : (ci > max_i ? max_i : ci);
-                    out_i = (float)ci;
-                }
+                if (bad) raise_status(a.status, LSS_ERR_RANGE_INDEX);
+                else n_pulses = P + 1;
             }
         }
+    }
+
+    // ---- argmax of the summed waveform (simulation.py:148-153), warp-cooperative ------------------------------------
+    // Only samples inside some pulse window are non-zero.  Pulses whose windows overlap form a group whose samples are
+    // summed in full (in dict order, like the reference's i[k] +=); an isolated pulse A sin^2(pi (R - r)/(c tau)) is
+    // unimodal and symmetric about r + c tau / 2, so its maximum over the grid is at one of the three samples around
+    // the sample nearest to the peak.  The owner lane publishes its pulses and candidate segments in shared memory,
+    // the 32 lanes evaluate the candidate samples in parallel and reduce to the first maximum (np.argmax).
+    __shared__ double s_amp[SNOW_TPB / 32][LSS_MAX_OCC + 1];
+    __shared__ double s_r[SNOW_TPB / 32][LSS_MAX_OCC + 1];
+    __shared__ int s_win[SNOW_TPB / 32][LSS_MAX_OCC + 1];
+    __shared__ int4 s_seg[SNOW_TPB / 32][LSS_MAX_OCC + 2];       // first sample, first pulse, last pulse, prefix
+    double best = 0.0;
+    int kbest = 0;
+    {
+        const int wid = threadIdx.x >> 5;
+        unsigned todo = __ballot_sync(0xffffffffu, n_pulses > 0);
+        while (todo) {
+            const int owner = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int nseg = 0, T = 0;
+            if (lane == owner) {
+                const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
+                for (int j = 0; j < n_pulses; j++) {
+                    s_amp[wid][j] = ha1[j];
+                    s_r[wid][j] = hr[j];
+                    s_win[wid][j] = ks[j] | (ke[j] << 16);
+                }
+                int j = 0;
+                while (j < n_pulses) {
+                    int g1 = j, k_lo = ks[j], k_hi = ke[j];
+                    while (g1 + 1 < n_pulses && ks[g1 + 1] < k_hi) {
+                        g1++;
+                        k_lo = min(k_lo, ks[g1]);
+                        k_hi = max(k_hi, ke[g1]);
+                    }
+                    if (g1 == j) {
+                        const int k0 = (int)rint((hr[j] + ctau / 2) * inv_step);
+                        k_lo = max(k_lo, k0 - 1);
+                        k_hi = min(k_hi, k0 + 2);
+                    }
+                    if (k_hi > k_lo) {
+                        s_seg[wid][nseg] = make_int4(k_lo, j, g1, T);
+                        T += k_hi - k_lo;
+                        nseg++;
+                    }
+                    j = g1 + 1;
+                }
+            }
+            __syncwarp();
+            nseg = __shfl_sync(0xffffffffu, nseg, owner);
+            T = __shfl_sync(0xffffffffu, T, owner);
+            double bv = 0.0;
+            int bk = 0;
+            for (int c = lane; c < T; c += 32) {
+                int sgi = 0;
+                while (sgi + 1 < nseg && s_seg[wid][sgi + 1].w <= c) sgi++;
+                const int4 sg = s_seg[wid][sgi];
+                const int k = sg.x + (c - sg.w);
+                const double Rk = __ldg(&a.R[k]);
+                double v = 0.0;
+                for (int q = sg.y; q <= sg.z; q++) {
+                    const int wn = s_win[wid][q];
+                    if (k >= (wn & 0xffff) && k < (wn >> 16)) {
+                        const double sn = sin((LSS_PI * (Rk - s_r[wid][q])) / ctau);
+                        v += s_amp[wid][q] * (sn * sn);
+                    }
+                }
+                if (v > bv) { bv = v; bk = k; }               // ascending k per lane: first maximum
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, sh);
+                const int ok = __shfl_xor_sync(0xffffffffu, bk, sh);
+                if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+            }
+            if (lane == owner) { best = bv; kbest = bv > 0.0 ? bk : 0; }
+            __syncwarp();
+        }
+    }
+
+    if (n_pulses > 0) {
+        // ---- new range / intensity / label (simulation.py:151-188) -------------------------------------------------
+        const double max_i = a.sensor->max_intensity[ch];
+        const double min_i = a.sensor->min_intensity[ch];
+        const double i_orig = 0.9 * max_i;
+        const double d_max = ((double)kbest / 10) - (ctau / 2);
+        const double q1 = 1 - d_max / 120;
+        double i_max = best + max_i * a.sensor->focal_slope[ch] * fabs(a.sensor->focal_offset[ch] - q1 * q1);
+        i_max = i_max < min_i ? min_i : (i_max > max_i ? max_i : i_max);
+        const long long new_i = (long long)i_max;       // int(): truncation
+        if (fabs(d_max - d) < 2 * (1.0 / 10)) {
+            out_l = 1.0f;
+            diff = i_orig - (double)new_i;
+        } else {
+            out_l = 2.0f;
+            const double sc = d_max / d;
+            out_x = (float)((double)px * sc);
+            out_y = (float)((double)py * sc);
+            out_z = (float)((double)pz * sc);
+        }
+        if (new_i < 0) raise_status(a.status, LSS_ERR_NEGATIVE_INTENSITY);
+        double ci = (double)new_i;
+        ci = ci < min_i ? min_i : (ci > max_i ? max_i : ci);
+        out_i = (float)ci;
     }
 
     // ---- cloud-level post: round, threshold, FOV (simulation.py:516-540) ------------------------------------------
@@ -566,7 +617,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
 
     if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly) {
         // plane + laser parameters + threshold polynomial from the channel-sorted cloud (simulation.py:449-467)
-        lss_status ps = lss_prepass_run(e, d_pts_sorted, d_off, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, nullptr,
+        lss_status ps = lss_prepass_run(e, d_pts_sorted, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1, nullptr,
                                         d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, stream);
         if (ps != LSS_OK) return ps;
     }

@@ -405,7 +405,7 @@ def total_transmittance_from_ground(ain, nair=1.0003, nw=1.33, rho=0.9):
 
 def ground_water_augmentation(pointcloud, water_height=0.001, pavement_depth=0.0012, noise_floor=0.7, power_factor=15,
                               estimation_method='linear', flat_earth=False, delta=0.5, replace=True, plane=None,
-                              return_internals=False):
+                              return_internals=False, least_populated='argpartition'):
     """tools/wet_ground/augmentation.py:25-161 (debug plots dropped; `plane` lets a test inject the RANSAC result)."""
     w, h = calculate_plane(pointcloud) if plane is None else plane
     height_over_ground = np.matmul(pointcloud[:, :3], np.asarray(w))
@@ -424,7 +424,7 @@ def ground_water_augmentation(pointcloud, water_height=0.001, pavement_depth=0.0
                                    np.linalg.norm(pointcloud_planes[:, :3], axis=1) * np.linalg.norm([0, 0, 1])))
     relative_output_intensity, adaptive_noise_threshold, pfit, _ = estimate_laser_parameters(
         pointcloud_planes, ang, noise_floor=noise_floor, estimation_method=estimation_method,
-        power_factor=power_factor)
+        power_factor=power_factor, least_populated=least_populated)
     reflectivities = pointcloud_planes[:, 3] / np.cos(ang) / relative_output_intensity
     rs, ts, rp, tp, aaout = total_transmittance_from_ground(ang, rho=np.clip(reflectivities, 0.05, 1))
     t = np.maximum(tp, ts)

@@ -86,7 +86,7 @@ def test_augment_end_to_end_device_prepass(engine, oracle):
 def test_too_few_ground_points(engine):
     from lidar_snow_sim_b200.snowfall.simulation import augment
     pc = synthetic_cloud(seed=2, n_azimuth=64)
-    pc = pc[pc[:, 2] > -0.5]                                    # no ground returns at all
+    pc = pc[(pc[:, 2] > -0.5) & (pc[:, 2] < 0.9)]               # no ground returns, nothing near the flat-earth fallback plane
     tables = [synthetic_particles(k, 2000) for k in range(64)]
     with pytest.raises(TypeError):                              # estimate_laser_parameters -> None, simulation.py:457-462
         augment(pc, 'unused', DIV, only_camera_fov=False, engine=engine, tables=tables)
