@@ -1,13 +1,19 @@
 // snowfall.cu -- batched snowfall augmentation on device-resident clouds.
 //
 // Pipeline per call (all on one stream):
-//   k_channel_sort   stable counting sort of every cloud by channel        (tools/snowfall/simulation.py:447)
-//   k_snowfall       one thread per beam: range/azimuth, candidate scan of ONE azimuth bucket of the channel's
-//                    snowflake plane, exact float64 disk/wedge test, nearest-first claiming of the beam's angular
-//                    sub-intervals, summed sin^2 waveform + argmax, relabel / move the point, threshold + FOV keep
-//                    flag, per-cloud statistics                            (simulation.py:50-194, 231-424, 516-540)
-//   k_compact        stable stream compaction of the kept rows per cloud   (simulation.py:523,540)
-//   k_finalize       stats (num_attenuated, num_removed, avg_intensity_diff) (simulation.py:525-542)
+//   [pre-pass]       ground plane + noise-threshold polynomial (prepass.cu)     (tools/snowfall/simulation.py:449-467)
+//   k_snowfall       one thread per beam, beams in INPUT order: range/azimuth, candidate scan of ONE azimuth bucket of
+//                    the channel's snowflake plane, exact float64 disk/wedge test, nearest-first claiming of the beam's
+//                    angular sub-intervals; then, warp-cooperatively, the summed sin^2 waveform + argmax; relabel / move
+//                    the point, threshold + FOV keep flag, statistics, per-tile channel histogram of the kept rows
+//                                                                                 (simulation.py:50-194, 231-424, 516-540)
+//   k_tile_scan      per cloud: exclusive scan of the tile histograms -> destination of every (tile, channel) run;
+//                    kept-row count and stats (num_attenuated, num_removed, avg_intensity_diff)  (simulation.py:525-542)
+//   k_scatter        stable scatter of the kept rows to "sorted by channel, compacted" order -- the reference's
+//                    pc[pc[:, 4].argsort()] (simulation.py:447) and its boolean-mask filters (:523,540) in ONE pass
+//
+// The reference sorts first and filters last; both are pure row permutations/selections that commute with the per-beam
+// solve, so they are applied once, at the end (82 B/point of traffic instead of 122).
 //
 // Numerics: everything the reference computes in float32 under NumPy 2 (range d, azimuth theta, the hard target's
 // waveform window and r^2) is computed in float32 with round-to-nearest, non-fused intrinsics so it is bit-identical;
@@ -17,8 +23,10 @@
 namespace {
 
 constexpr int SNOW_TPB = 128;
-constexpr int SORT_TPB = 1024;
-constexpr int CHANNEL_BINS = LSS_N_CHANNELS + 1;   // + "not a valid channel"
+constexpr int SNOW_WARPS = SNOW_TPB / 32;
+constexpr int TILE = 1024;                          // rows per scatter tile
+constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
+constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
 
 struct DevArgs {
     // tables
@@ -29,8 +37,8 @@ struct DevArgs {
     int n_planes;
     double inv_w, w;
     // per call
-    const float *pts;            // channel-sorted rows
-    const float *theta;          // sorted theta or null
+    const float *pts;            // rows in input order
+    const float *theta;          // optional, input order
     const int64_t *cloud_off;    // [B+1] device
     const int32_t *order;        // [B*64] device
     const double *thresh;        // [B*3] device or null
@@ -40,97 +48,26 @@ struct DevArgs {
     double half_div;             // radians(beam_divergence / 2)
     double div_rad;              // radians(beam_divergence)
     uint32_t flags;
-    float *aug;                  // [N*5] un-compacted augmented rows
-    uint8_t *keep;               // [N]
-    int32_t *nocc;               // optional
+    float *aug;                  // [N*5] augmented rows, input order
+    uint8_t *code_keep;          // [N] channel bin of a kept row, 255 = dropped
+    uint8_t *code_all;           // optional [N] channel bin of every row (un-filtered debug output)
+    int32_t *nocc;               // optional [N], input order
+    unsigned *hist_keep;         // [sum of tiles * NBINS]; cloud b owns rows tile_base[b] .. tile_base[b+1]
+    unsigned *hist_all;          // optional
+    const int32_t *tile_base;    // [B+1] device
     double *stats;               // [B*4]: num_attenuated, num_removed, avg_diff, diff_sum
-    int *counters;               // [B*2]: num_attenuated(kept), num_removed
+    int *counters;               // [B*2]: num_attenuated (threshold-kept), num_removed
     int *status;
 };
 
 __device__ __forceinline__ void raise_status(int *status, int code) { atomicMax(status, code); }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// channel sort: one CTA per cloud, tiles of SORT_TPB rows processed in order => stable
-// ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int channel_bin(float ch)
 {
     int c = (int)ch;
     return (ch >= 0.0f && ch < 64.0f && (float)c == ch) ? c : LSS_N_CHANNELS;
 }
 
-__global__ void __launch_bounds__(SORT_TPB) k_channel_sort(const float *__restrict__ pts, const float *__restrict__ theta,
-                                                            const int64_t *__restrict__ cloud_off,
-                                                            float *__restrict__ sorted, float *__restrict__ theta_sorted,
-                                                            int32_t *__restrict__ perm)
-{
-    __shared__ int base[CHANNEL_BINS];
-    __shared__ int warp_cnt[SORT_TPB / 32][CHANNEL_BINS];
-    const int b = blockIdx.x;
-    const int64_t beg = cloud_off[b];
-    const int n = (int)(cloud_off[b + 1] - beg);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float *src = pts + beg * 5;
-
-    if (tid < CHANNEL_BINS) base[tid] = 0;
-    __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += SORT_TPB) {      // warp-aggregated histogram (sorted inputs hit one bin)
-        const int i = t0 + tid;
-        const int bin = i < n ? channel_bin(src[(int64_t)i * 5 + 4]) : CHANNEL_BINS;
-        const unsigned m = __match_any_sync(0xffffffffu, bin);
-        if (bin < CHANNEL_BINS && lane == __ffs(m) - 1) atomicAdd(&base[bin], __popc(m));
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int c = 0; c < CHANNEL_BINS; c++) { int t = base[c]; base[c] = run; run += t; }
-    }
-    __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += SORT_TPB) {
-        for (int k = tid; k < (SORT_TPB / 32) * CHANNEL_BINS; k += SORT_TPB) (&warp_cnt[0][0])[k] = 0;
-        __syncthreads();
-        const int i = t0 + tid;
-        float row[5];
-        int bin = CHANNEL_BINS;      // inactive
-        if (i < n) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) row[k] = src[(int64_t)i * 5 + k];
-            bin = channel_bin(row[4]);
-        }
-        unsigned m = __match_any_sync(0xffffffffu, bin);
-        int rank = __popc(m & ((1u << lane) - 1u));
-        if (bin < CHANNEL_BINS && rank == 0) warp_cnt[warp][bin] = __popc(m);
-        __syncthreads();
-        if (tid < CHANNEL_BINS) {
-            int run = base[tid];
-            for (int wv = 0; wv < SORT_TPB / 32; wv++) { int t = warp_cnt[wv][tid]; warp_cnt[wv][tid] = run; run += t; }
-            base[tid] = run;
-        }
-        __syncthreads();
-        if (i < n) {
-            int dst = warp_cnt[warp][bin] + rank;
-            float *o = sorted + (beg + dst) * 5;
-#pragma unroll
-            for (int k = 0; k < 5; k++) o[k] = row[k];
-            if (theta_sorted) theta_sorted[beg + dst] = theta[beg + i];
-            if (perm) perm[beg + dst] = i;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void k_identity_perm(const int64_t *__restrict__ cloud_off, int32_t *__restrict__ perm)
-{
-    const int b = blockIdx.y;
-    const int64_t beg = cloud_off[b];
-    const int n = (int)(cloud_off[b + 1] - beg);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) perm[beg + i] = i;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// per-beam solve
-// ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool within(double diff, double tol)
 {
     return (fabs(diff) < tol) || (fabs(diff - LSS_TWO_PI) < tol) || (fabs(diff + LSS_TWO_PI) < tol);
@@ -156,18 +93,44 @@ __device__ __forceinline__ double xsi32(float r)
     return (double)__fadd_rn(__fmul_rn((float)m, r), (float)b);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// per-beam solve
+// ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
 {
+    __shared__ float s_rows[SNOW_TPB * 5];                         // coalesced staging of the block's rows (in and out)
+    __shared__ double s_amp[SNOW_WARPS][POOL];
+    __shared__ double s_r[SNOW_WARPS][POOL];
+    __shared__ int s_win[SNOW_WARPS][POOL];
+    __shared__ int4 s_seg[SNOW_WARPS][POOL];                       // first sample, first pulse, last pulse, candidate prefix
+    __shared__ int s_cand_off[SNOW_WARPS][33];
+    __shared__ int s_seg_base[SNOW_WARPS][32];
+    __shared__ int s_nseg[SNOW_WARPS][32];
+    __shared__ double s_best[SNOW_WARPS][32];
+    __shared__ int s_kbest[SNOW_WARPS][32];
+
     const int b = blockIdx.y;
     const int64_t beg = a.cloud_off[b];
     const int n = (int)(a.cloud_off[b + 1] - beg);
-    const int i = blockIdx.x * SNOW_TPB + threadIdx.x;
+    const int blk0 = blockIdx.x * SNOW_TPB;
+    if (blk0 >= n) return;
+    const int i = blk0 + threadIdx.x;
     const bool active = i < n;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
+    {   // coalesced load of up to 128 rows (640 floats)
+        const float *src = a.pts + (beg + blk0) * 5;
+        const int nf = min(SNOW_TPB, n - blk0) * 5;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int f = q * SNOW_TPB + threadIdx.x;
+            if (f < nf) s_rows[f] = src[f];
+        }
+    }
+    __syncthreads();
     float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
     if (active) {
-        const float *row = a.pts + (beg + i) * 5;
+        const float *row = s_rows + 5 * threadIdx.x;
         px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
     }
     // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
@@ -271,7 +234,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                 double nlo = lo, nhi = hi;      // merge [lo, hi] into the union (absorb overlapping / touching pieces)
                 int w = 0;
                 for (int u = 0; u < nu; u++) {
-                    if (ulo[u] <= nhi && uhi[u] >= nlo && ulo[u] <= hi && uhi[u] >= lo) {
+                    if (ulo[u] <= hi && uhi[u] >= lo) {
                         nlo = fmin(nlo, ulo[u]);
                         nhi = fmax(nhi, uhi[u]);
                     } else {
@@ -321,32 +284,33 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
     // Only samples inside some pulse window are non-zero.  Pulses whose windows overlap form a group whose samples are
     // summed in full (in dict order, like the reference's i[k] +=); an isolated pulse A sin^2(pi (R - r)/(c tau)) is
     // unimodal and symmetric about r + c tau / 2, so its maximum over the grid is at one of the three samples around
-    // the sample nearest to the peak.  The owner lane publishes its pulses and candidate segments in shared memory,
-    // the 32 lanes evaluate the candidate samples in parallel and reduce to the first maximum (np.argmax).
-    __shared__ double s_amp[SNOW_TPB / 32][LSS_MAX_OCC + 1];
-    __shared__ double s_r[SNOW_TPB / 32][LSS_MAX_OCC + 1];
-    __shared__ int s_win[SNOW_TPB / 32][LSS_MAX_OCC + 1];
-    __shared__ int4 s_seg[SNOW_TPB / 32][LSS_MAX_OCC + 2];       // first sample, first pulse, last pulse, prefix
-    double best = 0.0;
-    int kbest = 0;
+    // the sample nearest to the peak.  Every lane publishes its pulses and candidate segments in the warp's pool; the
+    // candidates of all beams of the warp are then evaluated 32 at a time and reduced per beam with a segmented scan
+    // (first maximum wins, np.argmax).
+    s_best[wid][lane] = 0.0;
+    s_kbest[wid][lane] = 0;
     {
-        const int wid = threadIdx.x >> 5;
-        unsigned todo = __ballot_sync(0xffffffffu, n_pulses > 0);
-        while (todo) {
-            const int owner = __ffs(todo) - 1;
-            todo &= todo - 1;
+        unsigned remaining = __ballot_sync(0xffffffffu, n_pulses > 0);
+        while (remaining) {
+            const int mine = ((remaining >> lane) & 1u) ? n_pulses : 0;
+            int incl = mine;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += t; }
+            const bool in_batch = mine > 0 && incl <= POOL;          // a prefix of the remaining lanes (each <= 49)
+            remaining &= ~__ballot_sync(0xffffffffu, in_batch);
+            const int poff = incl - mine;
             int nseg = 0, T = 0;
-            if (lane == owner) {
+            if (in_batch) {
                 const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
-                for (int j = 0; j < n_pulses; j++) {
-                    s_amp[wid][j] = ha1[j];
-                    s_r[wid][j] = hr[j];
-                    s_win[wid][j] = ks[j] | (ke[j] << 16);
+                for (int j = 0; j < mine; j++) {
+                    s_amp[wid][poff + j] = ha1[j];
+                    s_r[wid][poff + j] = hr[j];
+                    s_win[wid][poff + j] = ks[j] | (ke[j] << 16);
                 }
                 int j = 0;
-                while (j < n_pulses) {
+                while (j < mine) {
                     int g1 = j, k_lo = ks[j], k_hi = ke[j];
-                    while (g1 + 1 < n_pulses && ks[g1 + 1] < k_hi) {
+                    while (g1 + 1 < mine && ks[g1 + 1] < k_hi) {
                         g1++;
                         k_lo = min(k_lo, ks[g1]);
                         k_hi = max(k_hi, ke[g1]);
@@ -357,47 +321,68 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                         k_hi = min(k_hi, k0 + 2);
                     }
                     if (k_hi > k_lo) {
-                        s_seg[wid][nseg] = make_int4(k_lo, j, g1, T);
+                        s_seg[wid][poff + nseg] = make_int4(k_lo, poff + j, poff + g1, T);
                         T += k_hi - k_lo;
                         nseg++;
                     }
                     j = g1 + 1;
                 }
             }
+            int cincl = T;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cincl, s); if (lane >= s) cincl += t; }
+            s_cand_off[wid][lane] = cincl - T;
+            if (lane == 31) s_cand_off[wid][32] = cincl;
+            s_seg_base[wid][lane] = poff;
+            s_nseg[wid][lane] = nseg;
+            const int total = __shfl_sync(0xffffffffu, cincl, 31);
             __syncwarp();
-            nseg = __shfl_sync(0xffffffffu, nseg, owner);
-            T = __shfl_sync(0xffffffffu, T, owner);
-            double bv = 0.0;
-            int bk = 0;
-            for (int c = lane; c < T; c += 32) {
-                int sgi = 0;
-                while (sgi + 1 < nseg && s_seg[wid][sgi + 1].w <= c) sgi++;
-                const int4 sg = s_seg[wid][sgi];
-                const int k = sg.x + (c - sg.w);
-                const double Rk = __ldg(&a.R[k]);
+            for (int base = 0; base < total; base += 32) {
+                const int c = base + lane;
+                int owner = -1, k = 0;
                 double v = 0.0;
-                for (int q = sg.y; q <= sg.z; q++) {
-                    const int wn = s_win[wid][q];
-                    if (k >= (wn & 0xffff) && k < (wn >> 16)) {
-                        const double sn = sin((LSS_PI * (Rk - s_r[wid][q])) / ctau);
-                        v += s_amp[wid][q] * (sn * sn);
+                if (c < total) {
+                    int lo = 0, hi = 32;                         // largest lane whose first candidate is <= c
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_cand_off[wid][mid] <= c) lo = mid; else hi = mid;
+                    }
+                    owner = lo;
+                    const int cl = c - s_cand_off[wid][owner];
+                    const int sb = s_seg_base[wid][owner], ns = s_nseg[wid][owner];
+                    int sgi = 0;
+                    while (sgi + 1 < ns && s_seg[wid][sb + sgi + 1].w <= cl) sgi++;
+                    const int4 sg = s_seg[wid][sb + sgi];
+                    k = sg.x + (cl - sg.w);
+                    const double Rk = __ldg(&a.R[k]);
+                    for (int q = sg.y; q <= sg.z; q++) {
+                        const int wn = s_win[wid][q];
+                        if (k >= (wn & 0xffff) && k < (wn >> 16)) {
+                            const double sn = sin((LSS_PI * (Rk - s_r[wid][q])) / ctau);
+                            v += s_amp[wid][q] * (sn * sn);
+                        }
                     }
                 }
-                if (v > bv) { bv = v; bk = k; }               // ascending k per lane: first maximum
-            }
+                // segmented inclusive scan over lanes of the same beam: candidates are ordered by (beam, sample)
 #pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, sh);
-                const int ok = __shfl_xor_sync(0xffffffffu, bk, sh);
-                if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+                for (int s = 1; s < 32; s <<= 1) {
+                    const double ov = __shfl_up_sync(0xffffffffu, v, s);
+                    const int ok = __shfl_up_sync(0xffffffffu, k, s);
+                    const int oo = __shfl_up_sync(0xffffffffu, owner, s);
+                    if (lane >= s && oo == owner && (ov > v || (ov == v && ok < k))) { v = ov; k = ok; }
+                }
+                const int nxt = __shfl_down_sync(0xffffffffu, owner, 1);
+                const bool tail = owner >= 0 && (lane == 31 || nxt != owner);
+                if (tail && v > s_best[wid][owner]) { s_best[wid][owner] = v; s_kbest[wid][owner] = k; }
+                __syncwarp();
             }
-            if (lane == owner) { best = bv; kbest = bv > 0.0 ? bk : 0; }
-            __syncwarp();
         }
     }
 
     if (n_pulses > 0) {
         // ---- new range / intensity / label (simulation.py:151-188) -------------------------------------------------
+        const double best = s_best[wid][lane];
+        const int kbest = best > 0.0 ? s_kbest[wid][lane] : 0;
         const double max_i = a.sensor->max_intensity[ch];
         const double min_i = a.sensor->min_intensity[ch];
         const double i_orig = 0.9 * max_i;
@@ -450,10 +435,39 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                    (depth >= 0.0f);
         }
         removed = !keep;
-        float *o = a.aug + (beg + i) * 5;
-        o[0] = out_x; o[1] = out_y; o[2] = out_z; o[3] = out_i; o[4] = out_l;
-        a.keep[beg + i] = keep ? 1 : 0;
+        a.code_keep[beg + i] = keep ? (uint8_t)ch : (uint8_t)255;
+        if (a.code_all) a.code_all[beg + i] = (uint8_t)ch;
         if (a.nocc) a.nocc[beg + i] = n_claim;
+    }
+    // augmented rows back through shared memory (coalesced store)
+    __syncthreads();
+    if (active) {
+        float *row = s_rows + 5 * threadIdx.x;
+        row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
+    }
+    __syncthreads();
+    {
+        float *dst = a.aug + (beg + blk0) * 5;
+        const int nf = min(SNOW_TPB, n - blk0) * 5;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int f = q * SNOW_TPB + threadIdx.x;
+            if (f < nf) dst[f] = s_rows[f];
+        }
+    }
+    // per-tile channel histograms for the scatter pass (warp-aggregated)
+    {
+        const int tile = blk0 / TILE;
+        unsigned *hk = a.hist_keep + ((size_t)a.tile_base[b] + tile) * NBINS;
+        const int ck = (active && keep) ? ch : -1;
+        const unsigned mk = __match_any_sync(0xffffffffu, ck);
+        if (ck >= 0 && lane == __ffs(mk) - 1) atomicAdd(&hk[ck], (unsigned)__popc(mk));
+        if (a.hist_all) {
+            unsigned *ha = a.hist_all + ((size_t)a.tile_base[b] + tile) * NBINS;
+            const int ca = active ? ch : -1;
+            const unsigned ma = __match_any_sync(0xffffffffu, ca);
+            if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&ha[ca], (unsigned)__popc(ma));
+        }
     }
     // per-cloud statistics: warp-aggregated
     const unsigned m_att = __ballot_sync(0xffffffffu, keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS);
@@ -468,78 +482,117 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// stable compaction, one CTA per cloud
+// tile scan: hist[tile][bin] -> exclusive destination offsets in (bin-major, tile-minor) order.  One CTA per cloud,
+// one warp per bin at a time, tiles scanned 32 at a time.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_TPB) k_compact(const float *__restrict__ aug, const uint8_t *__restrict__ keep,
-                                                       const int64_t *__restrict__ cloud_off, float *__restrict__ out,
-                                                       int32_t *__restrict__ counts)
+__global__ void __launch_bounds__(1024) k_tile_scan(unsigned *hist, const int32_t *__restrict__ tile_base,
+                                                     int32_t *counts /* or null */, double *stats, const int *counters)
 {
-    __shared__ int warp_tot[SORT_TPB / 32];
-    __shared__ int run_s;
+    __shared__ unsigned bin_total[NBINS];
     const int b = blockIdx.x;
-    const int64_t beg = cloud_off[b];
-    const int n = (int)(cloud_off[b + 1] - beg);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) run_s = 0;
-    __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += SORT_TPB) {
-        const int i = t0 + tid;
-        const bool k = (i < n) && keep[beg + i];
-        const unsigned m = __ballot_sync(0xffffffffu, k);
-        const int rank = __popc(m & ((1u << lane) - 1u));
-        if (lane == 0) warp_tot[warp] = __popc(m);
-        __syncthreads();
-        int off = run_s;
-        for (int wv = 0; wv < warp; wv++) off += warp_tot[wv];
-        if (k) {
-            const float *s = aug + (beg + i) * 5;
-            float *o = out + (beg + off + rank) * 5;
+    const int n_tiles = tile_base[b + 1] - tile_base[b];
+    unsigned *h = hist + (size_t)tile_base[b] * NBINS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < NBINS; c += 32) {
+        unsigned run = 0;
+        for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+            const int t = t0 + lane;
+            const unsigned v = t < n_tiles ? h[(size_t)t * NBINS + c] : 0u;
+            unsigned incl = v;
 #pragma unroll
-            for (int q = 0; q < 5; q++) o[q] = s[q];
+            for (int s = 1; s < 32; s <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += o; }
+            if (t < n_tiles) h[(size_t)t * NBINS + c] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int wv = 0; wv < SORT_TPB / 32; wv++) t += warp_tot[wv];
-            run_s += t;
-        }
-        __syncthreads();
+        if (lane == 0) bin_total[c] = run;
     }
-    if (tid == 0) counts[b] = run_s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int c = 0; c < NBINS; c++) { const unsigned t = bin_total[c]; bin_total[c] = run; run += t; }
+        if (counts) counts[b] = (int32_t)run;
+        if (stats) {
+            const int n_att = counters[2 * b], n_rem = counters[2 * b + 1];
+            const double sum = stats[4 * b + 3];
+            stats[4 * b + 0] = (double)n_att;
+            stats[4 * b + 1] = (double)n_rem;
+            stats[4 * b + 2] = n_att > 0 ? (double)(long long)(sum / (double)n_att) : 0.0;   // int(sum / n), :527-530
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_tiles * NBINS; k += blockDim.x) h[k] += bin_total[k % NBINS];
 }
 
-__global__ void k_finalize(double *stats, const int *counters, int n_clouds)
+// ---------------------------------------------------------------------------------------------------------------------
+// stable scatter of one tile: row i with code c goes to tile_off[tile][c] + (number of earlier rows of the tile with
+// the same code).  Grid (tiles, clouds), 1024 threads.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE) k_scatter(const float *__restrict__ aug, const uint8_t *__restrict__ code,
+                                                   const unsigned *__restrict__ tile_off,
+                                                   const int64_t *__restrict__ cloud_off,
+                                                   const int32_t *__restrict__ tile_base,
+                                                   float *__restrict__ out, const int32_t *__restrict__ nocc_in,
+                                                   int32_t *__restrict__ nocc_out, int32_t *__restrict__ perm_out)
 {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_clouds) return;
-    const int n_att = counters[2 * b], n_rem = counters[2 * b + 1];
-    const double sum = stats[4 * b + 3];
-    stats[4 * b + 0] = (double)n_att;
-    stats[4 * b + 1] = (double)n_rem;
-    stats[4 * b + 2] = n_att > 0 ? (double)(long long)(sum / (double)n_att) : 0.0;   // int(sum / n), :527-530
+    __shared__ unsigned warp_cnt[TILE / 32][NBINS];
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int64_t beg = cloud_off[b];
+    const int n = (int)(cloud_off[b + 1] - beg);
+    const int i = tile * TILE + threadIdx.x;
+    if (tile * TILE >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < (TILE / 32) * NBINS; k += TILE) (&warp_cnt[0][0])[k] = 0;
+    __syncthreads();
+    int c = -1;
+    if (i < n) {
+        const int cc = code[beg + i];
+        c = cc < NBINS ? cc : -1;
+    }
+    const unsigned m = __match_any_sync(0xffffffffu, c);
+    const int rank = __popc(m & ((1u << lane) - 1u));
+    if (c >= 0 && rank == 0) warp_cnt[warp][c] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x < NBINS) {
+        unsigned run = tile_off[((size_t)tile_base[b] + tile) * NBINS + threadIdx.x];
+        for (int wv = 0; wv < TILE / 32; wv++) { const unsigned t = warp_cnt[wv][threadIdx.x]; warp_cnt[wv][threadIdx.x] = run; run += t; }
+    }
+    __syncthreads();
+    if (c >= 0) {
+        const int64_t dst = beg + warp_cnt[warp][c] + rank;
+        const float *s = aug + (beg + i) * 5;
+        float *o = out + dst * 5;
+#pragma unroll
+        for (int q = 0; q < 5; q++) o[q] = s[q];
+        if (nocc_out) nocc_out[dst] = nocc_in[beg + i];
+        if (perm_out) perm_out[dst] = i;
+    }
 }
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-    int64_t sorted, theta, keep, perm, aug, cloud_off, order, thresh, counters, prepass, prepass_bytes, total;
+    int64_t aug, code_keep, code_all, nocc, hist_keep, hist_all, hist_rows, cloud_off, tile_base, order, thresh, counters,
+        prepass, prepass_bytes, total;
 };
 
 WsLayout ws_layout(int64_t n_total, int n_clouds)
 {
     WsLayout w;
+    w.hist_rows = n_total / TILE + (int64_t)n_clouds + 1;          // >= sum over clouds of ceil(n_b / TILE)
     int64_t o = 0;
-    w.sorted = o;    o = align_up(o + n_total * 5 * 4, 256);
-    w.theta = o;     o = align_up(o + n_total * 4, 256);
-    w.keep = o;      o = align_up(o + n_total, 256);
-    w.perm = o;      o = align_up(o + n_total * 4, 256);
-    w.aug = o;       o = align_up(o + n_total * 5 * 4, 256);
-    w.cloud_off = o; o = align_up(o + (int64_t)(n_clouds + 1) * 8, 256);
-    w.order = o;     o = align_up(o + (int64_t)n_clouds * LSS_N_CHANNELS * 4, 256);
-    w.thresh = o;    o = align_up(o + (int64_t)n_clouds * 3 * 8, 256);
-    w.counters = o;  o = align_up(o + (int64_t)n_clouds * 2 * 4, 256);
+    w.aug = o;        o = align_up(o + n_total * 5 * 4, 256);
+    w.code_keep = o;  o = align_up(o + n_total, 256);
+    w.code_all = o;   o = align_up(o + n_total, 256);
+    w.nocc = o;       o = align_up(o + n_total * 4, 256);
+    w.hist_keep = o;  o = align_up(o + w.hist_rows * NBINS * 4, 256);
+    w.hist_all = o;   o = align_up(o + w.hist_rows * NBINS * 4, 256);
+    w.cloud_off = o;  o = align_up(o + (int64_t)(n_clouds + 1) * 8, 256);
+    w.tile_base = o;  o = align_up(o + (int64_t)(n_clouds + 1) * 4, 256);
+    w.order = o;      o = align_up(o + (int64_t)n_clouds * LSS_N_CHANNELS * 4, 256);
+    w.thresh = o;     o = align_up(o + (int64_t)n_clouds * 3 * 8, 256);
+    w.counters = o;   o = align_up(o + (int64_t)n_clouds * 2 * 4, 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
-    w.prepass = o;   o = align_up(o + w.prepass_bytes, 256);
+    w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
     return w;
 }
@@ -576,19 +629,29 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     const double div_rad = s.beam_divergence_deg * (LSS_PI / 180.0);
     if (!(div_rad > 0) || div_rad > s.ts->max_div_rad * (1 + 1e-12))
         return lss_fail(e, LSS_ERR_INVALID_ARG, "beam_divergence exceeds the value the table set was built for");
+    const int max_tiles = (int)((max_n + TILE - 1) / TILE);
+    std::vector<int32_t> h_tile_base(B + 1, 0);
+    for (int b = 0; b < B; b++)
+        h_tile_base[b + 1] = h_tile_base[b] + (int32_t)((s.h_cloud_offsets[b + 1] - s.h_cloud_offsets[b] + TILE - 1) / TILE);
+    if ((s.d_out_perm || s.d_out_nocc) && !s.d_out_full)
+        return lss_fail(e, LSS_ERR_INVALID_ARG, "d_out_perm / d_out_nocc need d_out_full");
 
     char *ws = (char *)s.d_workspace;
-    float *d_sorted = (float *)(ws + w.sorted);
-    float *d_theta_sorted = (float *)(ws + w.theta);
-    uint8_t *d_keep = (uint8_t *)(ws + w.keep);
-    int32_t *d_perm = s.d_out_perm ? s.d_out_perm : (int32_t *)(ws + w.perm);
-    float *d_aug = s.d_out_full ? s.d_out_full : (float *)(ws + w.aug);
+    float *d_aug = (float *)(ws + w.aug);
+    uint8_t *d_code_keep = (uint8_t *)(ws + w.code_keep);
+    const bool want_all = s.d_out_full != nullptr;
+    uint8_t *d_code_all = want_all ? (uint8_t *)(ws + w.code_all) : nullptr;
+    int32_t *d_nocc_tmp = s.d_out_nocc ? (int32_t *)(ws + w.nocc) : nullptr;
+    unsigned *d_hist_keep = (unsigned *)(ws + w.hist_keep);
+    unsigned *d_hist_all = want_all ? (unsigned *)(ws + w.hist_all) : nullptr;
     int64_t *d_off = (int64_t *)(ws + w.cloud_off);
+    int32_t *d_tile_base = (int32_t *)(ws + w.tile_base);
     int32_t *d_order = (int32_t *)(ws + w.order);
     double *d_thresh = (double *)(ws + w.thresh);
     int *d_counters = (int *)(ws + w.counters);
 
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, s.h_cloud_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, stream));
+    LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_tile_base, h_tile_base.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, stream));
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_order, s.h_order, sizeof(int32_t) * B * LSS_N_CHANNELS, cudaMemcpyHostToDevice, stream));
     if (s.h_thresh_poly)
         LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_thresh, s.h_thresh_poly, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, stream));
@@ -598,27 +661,14 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         if (B) LSS_CUDA_CHECK(e, cudaMemsetAsync(s.d_out_counts, 0, sizeof(int32_t) * B, stream));
         return LSS_OK;
     }
-
-    const float *d_pts_sorted = s.d_points;
-    const float *d_theta = s.d_theta;
-    if (!(s.flags & LSS_FLAG_ASSUME_SORTED)) {
-        {
-            KernelTimer kt(e, LSS_K_SORT, stream);
-            k_channel_sort<<<B, SORT_TPB, 0, stream>>>(s.d_points, s.d_theta, d_off, d_sorted,
-                                                       s.d_theta ? d_theta_sorted : nullptr, d_perm);
-        }
-        d_pts_sorted = d_sorted;
-        d_theta = s.d_theta ? d_theta_sorted : nullptr;
-    } else if (s.d_out_perm) {
-        dim3 g((unsigned)((max_n + 255) / 256), B);
-        KernelTimer kt(e, LSS_K_SORT, stream);
-        k_identity_perm<<<g, 256, 0, stream>>>(d_off, d_perm);
-    }
+    const size_t hist_bytes = (size_t)h_tile_base[B] * NBINS * sizeof(unsigned);
+    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_hist_keep, 0, hist_bytes, stream));
+    if (d_hist_all) LSS_CUDA_CHECK(e, cudaMemsetAsync(d_hist_all, 0, hist_bytes, stream));
 
     if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly) {
-        // plane + laser parameters + threshold polynomial from the channel-sorted cloud (simulation.py:449-467)
-        lss_status ps = lss_prepass_run(e, d_pts_sorted, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1, nullptr,
-                                        d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, stream);
+        // plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given
+        lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
+                                        nullptr, d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, stream);
         if (ps != LSS_OK) return ps;
     }
 
@@ -630,8 +680,8 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.n_planes = s.ts->n_planes;
     a.w = LSS_TWO_PI / s.ts->n_buckets;
     a.inv_w = s.ts->n_buckets / LSS_TWO_PI;
-    a.pts = d_pts_sorted;
-    a.theta = d_theta;
+    a.pts = s.d_points;
+    a.theta = s.d_theta;
     a.cloud_off = d_off;
     a.order = d_order;
     a.thresh = d_thresh;
@@ -642,23 +692,35 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.div_rad = div_rad;
     a.flags = s.flags;
     a.aug = d_aug;
-    a.keep = d_keep;
-    a.nocc = s.d_out_nocc;
+    a.code_keep = d_code_keep;
+    a.code_all = d_code_all;
+    a.nocc = d_nocc_tmp;
+    a.hist_keep = d_hist_keep;
+    a.hist_all = d_hist_all;
+    a.tile_base = d_tile_base;
     a.stats = s.d_out_stats;
     a.counters = d_counters;
     a.status = e->d_status;
-    dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
+        dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
         k_snowfall<<<grid, SNOW_TPB, 0, stream>>>(a);
     }
     {
-        KernelTimer kt(e, LSS_K_COMPACT, stream);
-        k_compact<<<B, SORT_TPB, 0, stream>>>(d_aug, d_keep, d_off, s.d_out_points, s.d_out_counts);
+        KernelTimer kt(e, LSS_K_SORT, stream);
+        k_tile_scan<<<B, 1024, 0, stream>>>(d_hist_keep, d_tile_base, s.d_out_counts, s.d_out_stats, d_counters);
     }
     {
-        KernelTimer kt(e, LSS_K_FINALIZE, stream);
-        k_finalize<<<(B + 127) / 128, 128, 0, stream>>>(s.d_out_stats, d_counters, B);
+        KernelTimer kt(e, LSS_K_COMPACT, stream);
+        k_scatter<<<dim3(max_tiles, B), TILE, 0, stream>>>(d_aug, d_code_keep, d_hist_keep, d_off, d_tile_base,
+                                                           s.d_out_points, nullptr, nullptr, nullptr);
+    }
+    if (want_all) {     // un-filtered, channel-sorted debug views (tests): full rows, original index, occluder counts
+        KernelTimer kt(e, LSS_K_COMPACT, stream);
+        k_tile_scan<<<B, 1024, 0, stream>>>(d_hist_all, d_tile_base, nullptr, nullptr, nullptr);
+        k_scatter<<<dim3(max_tiles, B), TILE, 0, stream>>>(d_aug, d_code_all, d_hist_all, d_off, d_tile_base, s.d_out_full,
+                                                           d_nocc_tmp, s.d_out_nocc, s.d_out_perm);
+        e->launches++;
     }
     LSS_CUDA_CHECK(e, cudaGetLastError());
     return LSS_OK;

@@ -140,6 +140,7 @@ class SnowfallEngine:
             flags |= _lib.FLAG_DEVICE_PREPASS
         if assume_sorted:
             flags |= _lib.FLAG_ASSUME_SORTED
+        want_full = want_full or want_perm or want_nocc      # the debug views are produced together
         tp = None
         if thresh_poly is not None:
             tp = np.ascontiguousarray(thresh_poly, dtype=np.float64).reshape(B, 3)
