@@ -39,6 +39,9 @@ struct PreArgs {
     int have_plane;          // plane supplied by the caller
     CloudPre *cp;
     float *win;              // [N*3] compacted window points of each cloud at its own offset
+    float *stage;            // [N*3] per-tile staging of the window compaction
+    int *tile_cnt;           // [sum of tiles] window points per 1024-row tile
+    const int32_t *tile_base;   // [B+1] first tile of each cloud
     unsigned *hist;          // [B*50*2555]
     double *trial;           // [B*RANSAC_T*8]: n_inl, score, a, b, c, valid
     double *partial;         // [B * max_blocks * 16]
@@ -82,42 +85,77 @@ __device__ void block_sum(double (&v)[NV], double *smem /* [NV * warps] */)
         }
 }
 
-// ---- 1. mounting-window compaction (planes.py:21-27), one CTA per cloud, stable ---------------------------------------
-__global__ void __launch_bounds__(1024) k_window(PreArgs a)
+// ---- 1. mounting-window compaction (planes.py:21-27): stable, two kernels ----------------------------------------------
+// k_window_tiles (grid tiles x clouds): every 1024-row tile compacts its window points into its own staging slot;
+// k_window_gather (one CTA per cloud): scans the tile counts and gathers the few thousand points contiguously.
+constexpr int WTILE = 1024;
+
+__device__ __forceinline__ bool in_window(float x, float y, float z)
 {
-    __shared__ int warp_tot[32];
-    __shared__ int run_s;
-    const int b = blockIdx.x;
+    // float32 comparisons, python floats are weak scalars under NumPy 2
+    const float lim = __fsub_rn(-1.86f, __fmul_rn(0.01f, x));
+    return (z < -1.55f) && (z > lim) && (x > 10.0f) && (x < 70.0f) && (y > -3.0f) && (y < 3.0f);
+}
+
+__global__ void __launch_bounds__(WTILE) k_window_tiles(PreArgs a)
+{
+    __shared__ int warp_tot[WTILE / 32];
+    const int b = blockIdx.y, tile = blockIdx.x;
     const int64_t beg = a.cloud_off[b];
     const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
+    if (tile * WTILE >= n) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) run_s = 0;
-    __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += 1024) {
-        const int i = t0 + tid;
-        float x = 0, y = 0, z = 0;
-        bool in = false;
-        if (i < n) {
-            const float *r = a.pts + (beg + i) * 5;
-            x = r[0]; y = r[1]; z = r[2];
-            // float32 comparisons, python floats are weak scalars under NumPy 2
-            const float lim = __fsub_rn(-1.86f, __fmul_rn(0.01f, x));
-            in = (z < -1.55f) && (z > lim) && (x > 10.0f) && (x < 70.0f) && (y > -3.0f) && (y < 3.0f);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, in);
-        if (lane == 0) warp_tot[warp] = __popc(m);
-        __syncthreads();
-        int off = run_s;
-        for (int wv = 0; wv < warp; wv++) off += warp_tot[wv];
-        if (in) {
-            float *o = a.win + (beg + off + __popc(m & ((1u << lane) - 1u))) * 3;
-            o[0] = x; o[1] = y; o[2] = z;
-        }
-        __syncthreads();
-        if (tid == 0) { int t = 0; for (int wv = 0; wv < 32; wv++) t += warp_tot[wv]; run_s += t; }
-        __syncthreads();
+    const int i = tile * WTILE + tid;
+    float x = 0, y = 0, z = 0;
+    bool in = false;
+    if (i < n) {
+        const float *r = a.pts + (beg + i) * 5;
+        x = r[0]; y = r[1]; z = r[2];
+        in = in_window(x, y, z);
     }
-    if (tid == 0) a.cp[b].n_window = run_s;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = 0;
+    for (int wv = 0; wv < warp; wv++) off += warp_tot[wv];
+    if (in) {
+        float *o = a.stage + (beg + (int64_t)tile * WTILE + off + __popc(m & ((1u << lane) - 1u))) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+    }
+    if (tid == WTILE - 1) a.tile_cnt[a.tile_base[b] + tile] = off + warp_tot[warp];
+}
+
+__global__ void __launch_bounds__(1024) k_window_gather(PreArgs a)
+{
+    extern __shared__ int prefix[];            // [n_tiles + 1]
+    const int b = blockIdx.x;
+    const int64_t beg = a.cloud_off[b];
+    const int n_tiles = a.tile_base[b + 1] - a.tile_base[b];
+    const int *cnt = a.tile_cnt + a.tile_base[b];
+    const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
+    const int used_tiles = (n + WTILE - 1) / WTILE;
+    if (threadIdx.x < 32) {                    // one warp scans the tile counts
+        int run = 0;
+        for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+            const int t = t0 + threadIdx.x;
+            const int v = (t < used_tiles) ? cnt[t] : 0;
+            int incl = v;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, s); if ((int)threadIdx.x >= s) incl += o; }
+            if (t < n_tiles) prefix[t] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (threadIdx.x == 0) { prefix[n_tiles] = run; a.cp[b].n_window = run; }
+    }
+    __syncthreads();
+    const int K = prefix[n_tiles];
+    for (int o = threadIdx.x; o < K; o += blockDim.x) {
+        int lo = 0, hi = n_tiles;              // largest tile with prefix[tile] <= o
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= o) lo = mid; else hi = mid; }
+        const float *src = a.stage + (beg + (int64_t)lo * WTILE + (o - prefix[lo])) * 3;
+        float *dst = a.win + (beg + o) * 3;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
 }
 
 // ---- 2. median / MAD of the window heights: exact k-th element by 4-pass radix select ------------------------------------
@@ -254,19 +292,29 @@ __global__ void __launch_bounds__(PP_TPB) k_ransac_refit(PreArgs a)
     const int b = blockIdx.x;
     CloudPre &cp = a.cp[b];
     const int K = cp.n_window;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // most inliers, then highest score, then lowest trial index -- one warp, 4 trials per lane
         int best = -1;
         double bn = -1, bs = -1e301;
-        for (int t = 0; t < RANSAC_T && K > 5; t++) {
+        for (int t = threadIdx.x; t < RANSAC_T && K > 5; t += 32) {
             const double *tr = a.trial + ((size_t)b * RANSAC_T + t) * 8;
             if (tr[5] == 0.0) continue;
             if (tr[0] > bn || (tr[0] == bn && tr[1] > bs)) { bn = tr[0]; bs = tr[1]; best = t; }
         }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            const double on = __shfl_xor_sync(0xffffffffu, bn, sft), os = __shfl_xor_sync(0xffffffffu, bs, sft);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, sft);
+            const bool take = ob >= 0 && (best < 0 || on > bn || (on == bn && (os > bs || (os == bs && ob < best))));
+            if (take) { bn = on; bs = os; best = ob; }
+        }
+        if (threadIdx.x == 0) {
         cp.best_trial = best;
         bc[0] = (double)best;
         if (best >= 0) {
             const double *tr = a.trial + ((size_t)b * RANSAC_T + best) * 8;
             bc[1] = tr[2]; bc[2] = tr[3]; bc[3] = tr[4];
+        }
         }
     }
     __syncthreads();
@@ -373,16 +421,35 @@ __global__ void __launch_bounds__(PP_TPB) k_ground_stats(PreArgs a)
     }
 }
 
+// fixed-order reduction of the per-block partials: one warp per cloud, lane q owns partials q, q+32, ...
+template <int NV>
+__device__ __forceinline__ void warp_reduce_partials(const double *partial, int n_blocks, double (&v)[NV], double *vmax)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = 0.0;
+    double m = -1e300;
+    for (int q = lane; q < n_blocks; q += 32) {
+        const double *p = partial + (size_t)q * 16;
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] += p[k];
+        if (vmax) m = fmax(m, p[NV]);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], s);
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+    }
+    if (vmax) *vmax = m;
+}
+
 __global__ void k_ground_stats_final(PreArgs a, int n_blocks)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.n_clouds) return;
-    double v[5] = {0, 0, 0, 0, 0}, vmax = -1e300;
-    for (int q = 0; q < n_blocks; q++) {
-        const double *p = a.partial + ((size_t)b * a.max_blocks + q) * 16;
-        for (int k = 0; k < 5; k++) v[k] += p[k];
-        vmax = fmax(vmax, p[5]);
-    }
+    const int b = blockIdx.x;
+    double v[5], vmax;
+    warp_reduce_partials<5>(a.partial + (size_t)b * a.max_blocks * 16, n_blocks, v, &vmax);
+    if (threadIdx.x != 0) return;
     CloudPre &cp = a.cp[b];
     cp.n_ground = (int)v[0];
     cp.ymax = fabs(vmax);
@@ -511,14 +578,11 @@ __global__ void __launch_bounds__(PP_TPB) k_poly_sums(PreArgs a)
 
 __global__ void k_poly_solve(PreArgs a, int n_blocks, double *poly_out /* [B*3] or null */, double *plane_out /* [B*4] or null */)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.n_clouds) return;
+    const int b = blockIdx.x;
     CloudPre &cp = a.cp[b];
-    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int q = 0; q < n_blocks; q++) {
-        const double *p = a.partial + ((size_t)b * a.max_blocks + q) * 16;
-        for (int k = 0; k < 8; k++) s[k] += p[k];
-    }
+    double s[8];
+    warp_reduce_partials<8>(a.partial + (size_t)b * a.max_blocks * 16, n_blocks, s, nullptr);
+    if (threadIdx.x != 0) return;
     // normal equations for c0 + c1 t + c2 t^2, Gaussian elimination with partial pivoting
     double A[3][4] = {{s[0], s[1], s[2], s[5]}, {s[1], s[2], s[3], s[6]}, {s[2], s[3], s[4], s[7]}};
     bool ok = cp.n_ground >= 3;
@@ -550,7 +614,7 @@ inline int64_t align_up(int64_t v, int64_t al) { return (v + al - 1) / al * al; 
 
 }  // namespace
 
-struct PrepassLayout { int64_t cp, win, hist, trial, partial, plane_in, total; int max_blocks; };
+struct PrepassLayout { int64_t cp, win, stage, tile_cnt, tile_base, hist, trial, partial, plane_in, total; int max_blocks; };
 
 static PrepassLayout prepass_layout(int64_t n_total, int n_clouds)
 {
@@ -559,6 +623,9 @@ static PrepassLayout prepass_layout(int64_t n_total, int n_clouds)
     int64_t o = 0;
     L.cp = o;       o = align_up(o + (int64_t)sizeof(CloudPre) * n_clouds, 256);
     L.win = o;      o = align_up(o + n_total * 3 * 4, 256);
+    L.stage = o;    o = align_up(o + n_total * 3 * 4, 256);
+    L.tile_cnt = o; o = align_up(o + (n_total / 1024 + n_clouds + 1) * 4, 256);
+    L.tile_base = o; o = align_up(o + (int64_t)(n_clouds + 1) * 4, 256);
     L.hist = o;     o = align_up(o + (int64_t)n_clouds * HIST_NX * HIST_NY * 4, 256);
     L.trial = o;    o = align_up(o + (int64_t)n_clouds * RANSAC_T * 8 * 8, 256);
     L.partial = o;  o = align_up(o + (int64_t)n_clouds * L.max_blocks * 16 * 8, 256);
@@ -596,6 +663,9 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
     a.have_plane = h_plane_in != nullptr;
     a.cp = (CloudPre *)(ws + L.cp);
     a.win = (float *)(ws + L.win);
+    a.stage = (float *)(ws + L.stage);
+    a.tile_cnt = (int *)(ws + L.tile_cnt);
+    a.tile_base = (const int32_t *)(ws + L.tile_base);
     a.hist = (unsigned *)(ws + L.hist);
     a.trial = (double *)(ws + L.trial);
     a.partial = (double *)(ws + L.partial);
@@ -615,18 +685,28 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
             LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_plane, h_plane_in, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, stream));
             k_set_plane<<<(B + 127) / 128, 128, 0, stream>>>(a, d_plane);
         } else {
-            k_window<<<B, 1024, 0, stream>>>(a);
+            std::vector<int32_t> h_tb(B + 1, 0);
+            int max_tiles = 1;
+            for (int b = 0; b < B; b++) {
+                const int t = (int)((h_cloud_off[b + 1] - h_cloud_off[b] + WTILE - 1) / WTILE);
+                h_tb[b + 1] = h_tb[b] + t;
+                max_tiles = std::max(max_tiles, t);
+            }
+            LSS_CUDA_CHECK(e, cudaMemcpyAsync(ws + L.tile_base, h_tb.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, stream));
+            k_window_tiles<<<dim3(max_tiles, B), WTILE, 0, stream>>>(a);
+            k_window_gather<<<B, 1024, sizeof(int) * (max_tiles + 1), stream>>>(a);
+            e->launches++;
             k_window_mad<<<B, 1024, 0, stream>>>(a);
             k_ransac_trials<<<dim3(RANSAC_T, B), PP_TPB, 0, stream>>>(a);
             k_ransac_refit<<<B, PP_TPB, 0, stream>>>(a);
             e->launches += 3;
         }
         k_ground_stats<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
-        k_ground_stats_final<<<(B + 127) / 128, 128, 0, stream>>>(a, nblk);
+        k_ground_stats_final<<<B, 32, 0, stream>>>(a, nblk);
         k_ground_hist<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
         k_hist_minima<<<B, 1024, 0, stream>>>(a);
         k_poly_sums<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
-        k_poly_solve<<<(B + 127) / 128, 128, 0, stream>>>(a, nblk, d_poly_out, d_plane_out);
+        k_poly_solve<<<B, 32, 0, stream>>>(a, nblk, d_poly_out, d_plane_out);
         e->launches += 5;
     }
     LSS_CUDA_CHECK(e, cudaGetLastError());

@@ -27,6 +27,7 @@ constexpr int SNOW_WARPS = SNOW_TPB / 32;
 constexpr int TILE = 1024;                          // rows per scatter tile
 constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
 constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
+constexpr int CCAP = 512;                           // candidate samples a warp evaluates per cooperative batch
 
 struct DevArgs {
     // tables
@@ -57,6 +58,8 @@ struct DevArgs {
     const int32_t *tile_base;    // [B+1] device
     double *stats;               // [B*4]: num_attenuated, num_removed, avg_diff, diff_sum
     int *counters;               // [B*2]: num_attenuated (threshold-kept), num_removed
+    unsigned *att_cnt;           // [B*64] label-1 beams per channel (all of them, simulation.py:170)
+    unsigned long long *att_sum; // [B] sum of their new integer intensities
     int *status;
 };
 
@@ -98,14 +101,11 @@ __device__ __forceinline__ double xsi32(float r)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
 {
-    __shared__ float s_rows[SNOW_TPB * 5];                         // coalesced staging of the block's rows (in and out)
+    __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
     __shared__ double s_amp[SNOW_WARPS][POOL];
     __shared__ double s_r[SNOW_WARPS][POOL];
     __shared__ int s_win[SNOW_WARPS][POOL];
-    __shared__ int4 s_seg[SNOW_WARPS][POOL];                       // first sample, first pulse, last pulse, candidate prefix
-    __shared__ int s_cand_off[SNOW_WARPS][33];
-    __shared__ int s_seg_base[SNOW_WARPS][32];
-    __shared__ int s_nseg[SNOW_WARPS][32];
+    __shared__ unsigned s_cand[SNOW_WARPS][CCAP];                   // sample | first pulse << 11 | last pulse << 18 | lane << 25
     __shared__ double s_best[SNOW_WARPS][32];
     __shared__ int s_kbest[SNOW_WARPS][32];
 
@@ -118,19 +118,20 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
     const bool active = i < n;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-    {   // coalesced load of up to 128 rows (640 floats)
-        const float *src = a.pts + (beg + blk0) * 5;
-        const int nf = min(SNOW_TPB, n - blk0) * 5;
+    const int w0 = blk0 + 32 * wid;                                 // first row of this warp
+    const int nf_w = max(0, min(32, n - w0)) * 5;                   // floats of this warp's rows
+    {   // coalesced load of the warp's 32 rows (160 floats); no block-wide barrier anywhere in this kernel
+        const float *src = a.pts + (beg + w0) * 5;
 #pragma unroll
         for (int q = 0; q < 5; q++) {
-            const int f = q * SNOW_TPB + threadIdx.x;
-            if (f < nf) s_rows[f] = src[f];
+            const int f = q * 32 + lane;
+            if (f < nf_w) s_rows[wid][f] = src[f];
         }
     }
-    __syncthreads();
+    __syncwarp();
     float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
     if (active) {
-        const float *row = s_rows + 5 * threadIdx.x;
+        const float *row = &s_rows[wid][5 * lane];
         px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
     }
     // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
     const double d = (double)d32;
 
     float out_x = px, out_y = py, out_z = pz, out_i = pint, out_l = pch;
-    double diff = 0.0;
+    long long att_new_i = -1;    // >= 0: this beam was attenuated (label 1) to this integer intensity
     int n_claim = 0;
     const int ch = channel_bin(pch);
     const double ctau = 299792458.0 * 1e-8;
@@ -284,78 +285,93 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
     // Only samples inside some pulse window are non-zero.  Pulses whose windows overlap form a group whose samples are
     // summed in full (in dict order, like the reference's i[k] +=); an isolated pulse A sin^2(pi (R - r)/(c tau)) is
     // unimodal and symmetric about r + c tau / 2, so its maximum over the grid is at one of the three samples around
-    // the sample nearest to the peak.  Every lane publishes its pulses and candidate segments in the warp's pool; the
-    // candidates of all beams of the warp are then evaluated 32 at a time and reduced per beam with a segmented scan
-    // (first maximum wins, np.argmax).
+    // the sample nearest to the peak.  Every lane publishes its pulses and one descriptor per candidate sample in the
+    // warp's pool; the candidates of all beams of the warp are then evaluated 32 at a time and reduced per beam with a
+    // segmented scan (first maximum wins, np.argmax).
+    const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
+    // candidate segments of this beam: calls f(k_lo, k_hi, first pulse, last pulse) in ascending sample order
+    auto for_each_segment = [&](auto &&f) {
+        int j = 0;
+        while (j < n_pulses) {
+            int g1 = j, k_lo = ks[j], k_hi = ke[j];
+            while (g1 + 1 < n_pulses && ks[g1 + 1] < k_hi) {
+                g1++;
+                k_lo = min(k_lo, ks[g1]);
+                k_hi = max(k_hi, ke[g1]);
+            }
+            if (g1 == j) {
+                const int k0 = (int)rint((hr[j] + ctau / 2) * inv_step);
+                k_lo = max(k_lo, k0 - 1);
+                k_hi = min(k_hi, k0 + 2);
+            }
+            if (k_hi > k_lo) f(k_lo, k_hi, j, g1);
+            j = g1 + 1;
+        }
+    };
+    int T_all = 0;
+    if (n_pulses > 0) for_each_segment([&](int k_lo, int k_hi, int, int) { T_all += k_hi - k_lo; });
+    double best = 0.0;
+    int kbest = 0;
+    bool coop = n_pulses > 0;
+    if (T_all > CCAP) {          // pathological beam (dozens of overlapping pulses): solve it in this thread
+        coop = false;
+        for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
+            for (int k = k_lo; k < k_hi; k++) {
+                const double Rk = __ldg(&a.R[k]);
+                double v = 0.0;
+                for (int q = j0; q <= j1; q++)
+                    if (k >= ks[q] && k < ke[q]) {
+                        const double sn = sin((LSS_PI * (Rk - hr[q])) / ctau);
+                        v += ha1[q] * (sn * sn);
+                    }
+                if (v > best) { best = v; kbest = k; }
+            }
+        });
+    }
     s_best[wid][lane] = 0.0;
     s_kbest[wid][lane] = 0;
     {
-        unsigned remaining = __ballot_sync(0xffffffffu, n_pulses > 0);
+        unsigned remaining = __ballot_sync(0xffffffffu, coop);
         while (remaining) {
-            const int mine = ((remaining >> lane) & 1u) ? n_pulses : 0;
-            int incl = mine;
+            const bool rem = (remaining >> lane) & 1u;
+            const int mine = rem ? n_pulses : 0, myT = rem ? T_all : 0;
+            int incl = mine, cincl = myT;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += t; }
-            const bool in_batch = mine > 0 && incl <= POOL;          // a prefix of the remaining lanes (each <= 49)
-            remaining &= ~__ballot_sync(0xffffffffu, in_batch);
-            const int poff = incl - mine;
-            int nseg = 0, T = 0;
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, s);
+                const int u = __shfl_up_sync(0xffffffffu, cincl, s);
+                if (lane >= s) { incl += t; cincl += u; }
+            }
+            // a prefix of the remaining lanes (each has <= 49 pulses and <= CCAP candidates)
+            const bool in_batch = rem && incl <= POOL && cincl <= CCAP;
+            const unsigned batch = __ballot_sync(0xffffffffu, in_batch);
+            remaining &= ~batch;
+            const int total = __shfl_sync(0xffffffffu, cincl, 31 - __clz(batch));
             if (in_batch) {
-                const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
+                const int poff = incl - mine;
+                int coff = cincl - myT;
                 for (int j = 0; j < mine; j++) {
                     s_amp[wid][poff + j] = ha1[j];
                     s_r[wid][poff + j] = hr[j];
                     s_win[wid][poff + j] = ks[j] | (ke[j] << 16);
                 }
-                int j = 0;
-                while (j < mine) {
-                    int g1 = j, k_lo = ks[j], k_hi = ke[j];
-                    while (g1 + 1 < mine && ks[g1 + 1] < k_hi) {
-                        g1++;
-                        k_lo = min(k_lo, ks[g1]);
-                        k_hi = max(k_hi, ke[g1]);
-                    }
-                    if (g1 == j) {
-                        const int k0 = (int)rint((hr[j] + ctau / 2) * inv_step);
-                        k_lo = max(k_lo, k0 - 1);
-                        k_hi = min(k_hi, k0 + 2);
-                    }
-                    if (k_hi > k_lo) {
-                        s_seg[wid][poff + nseg] = make_int4(k_lo, poff + j, poff + g1, T);
-                        T += k_hi - k_lo;
-                        nseg++;
-                    }
-                    j = g1 + 1;
-                }
+                for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
+                    const unsigned hi_bits = ((unsigned)(poff + j0) << 11) | ((unsigned)(poff + j1) << 18) | ((unsigned)lane << 25);
+                    for (int k = k_lo; k < k_hi; k++) s_cand[wid][coff++] = (unsigned)k | hi_bits;
+                });
             }
-            int cincl = T;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) { const int t = __shfl_up_sync(0xffffffffu, cincl, s); if (lane >= s) cincl += t; }
-            s_cand_off[wid][lane] = cincl - T;
-            if (lane == 31) s_cand_off[wid][32] = cincl;
-            s_seg_base[wid][lane] = poff;
-            s_nseg[wid][lane] = nseg;
-            const int total = __shfl_sync(0xffffffffu, cincl, 31);
             __syncwarp();
             for (int base = 0; base < total; base += 32) {
                 const int c = base + lane;
                 int owner = -1, k = 0;
                 double v = 0.0;
                 if (c < total) {
-                    int lo = 0, hi = 32;                         // largest lane whose first candidate is <= c
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_cand_off[wid][mid] <= c) lo = mid; else hi = mid;
-                    }
-                    owner = lo;
-                    const int cl = c - s_cand_off[wid][owner];
-                    const int sb = s_seg_base[wid][owner], ns = s_nseg[wid][owner];
-                    int sgi = 0;
-                    while (sgi + 1 < ns && s_seg[wid][sb + sgi + 1].w <= cl) sgi++;
-                    const int4 sg = s_seg[wid][sb + sgi];
-                    k = sg.x + (cl - sg.w);
+                    const unsigned desc = s_cand[wid][c];
+                    k = desc & 2047u;
+                    owner = desc >> 25;
+                    const int q0 = (desc >> 11) & 127u, q1 = (desc >> 18) & 127u;
                     const double Rk = __ldg(&a.R[k]);
-                    for (int q = sg.y; q <= sg.z; q++) {
+                    for (int q = q0; q <= q1; q++) {
                         const int wn = s_win[wid][q];
                         if (k >= (wn & 0xffff) && k < (wn >> 16)) {
                             const double sn = sin((LSS_PI * (Rk - s_r[wid][q])) / ctau);
@@ -364,13 +380,14 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                     }
                 }
                 // segmented inclusive scan over lanes of the same beam: candidates are ordered by (beam, sample)
+                int ok_key = (owner << 16) | k;
 #pragma unroll
                 for (int s = 1; s < 32; s <<= 1) {
                     const double ov = __shfl_up_sync(0xffffffffu, v, s);
-                    const int ok = __shfl_up_sync(0xffffffffu, k, s);
-                    const int oo = __shfl_up_sync(0xffffffffu, owner, s);
-                    if (lane >= s && oo == owner && (ov > v || (ov == v && ok < k))) { v = ov; k = ok; }
+                    const int okey = __shfl_up_sync(0xffffffffu, ok_key, s);
+                    if (lane >= s && (okey >> 16) == owner && (ov > v || (ov == v && okey < ok_key))) { v = ov; ok_key = okey; }
                 }
+                k = ok_key & 0xffff;
                 const int nxt = __shfl_down_sync(0xffffffffu, owner, 1);
                 const bool tail = owner >= 0 && (lane == 31 || nxt != owner);
                 if (tail && v > s_best[wid][owner]) { s_best[wid][owner] = v; s_kbest[wid][owner] = k; }
@@ -378,14 +395,15 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
             }
         }
     }
+    if (coop) {
+        best = s_best[wid][lane];
+        kbest = best > 0.0 ? s_kbest[wid][lane] : 0;
+    }
 
     if (n_pulses > 0) {
         // ---- new range / intensity / label (simulation.py:151-188) -------------------------------------------------
-        const double best = s_best[wid][lane];
-        const int kbest = best > 0.0 ? s_kbest[wid][lane] : 0;
         const double max_i = a.sensor->max_intensity[ch];
         const double min_i = a.sensor->min_intensity[ch];
-        const double i_orig = 0.9 * max_i;
         const double d_max = ((double)kbest / 10) - (ctau / 2);
         const double q1 = 1 - d_max / 120;
         double i_max = best + max_i * a.sensor->focal_slope[ch] * fabs(a.sensor->focal_offset[ch] - q1 * q1);
@@ -393,7 +411,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
         const long long new_i = (long long)i_max;       // int(): truncation
         if (fabs(d_max - d) < 2 * (1.0 / 10)) {
             out_l = 1.0f;
-            diff = i_orig - (double)new_i;
+            att_new_i = new_i;                          // intensity_diff_sum += i_orig - new_i   (simulation.py:170)
         } else {
             out_l = 2.0f;
             const double sc = d_max / d;
@@ -440,19 +458,18 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
         if (a.nocc) a.nocc[beg + i] = n_claim;
     }
     // augmented rows back through shared memory (coalesced store)
-    __syncthreads();
+    __syncwarp();
     if (active) {
-        float *row = s_rows + 5 * threadIdx.x;
+        float *row = &s_rows[wid][5 * lane];
         row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
     }
-    __syncthreads();
+    __syncwarp();
     {
-        float *dst = a.aug + (beg + blk0) * 5;
-        const int nf = min(SNOW_TPB, n - blk0) * 5;
+        float *dst = a.aug + (beg + w0) * 5;
 #pragma unroll
         for (int q = 0; q < 5; q++) {
-            const int f = q * SNOW_TPB + threadIdx.x;
-            if (f < nf) dst[f] = s_rows[f];
+            const int f = q * 32 + lane;
+            if (f < nf_w) dst[f] = s_rows[wid][f];
         }
     }
     // per-tile channel histograms for the scatter pass (warp-aggregated)
@@ -469,15 +486,21 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
             if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&ha[ca], (unsigned)__popc(ma));
         }
     }
-    // per-cloud statistics: warp-aggregated
+    // per-cloud statistics: warp-aggregated integer atomics (order independent => bit-reproducible)
     const unsigned m_att = __ballot_sync(0xffffffffu, keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS);
     const unsigned m_rem = __ballot_sync(0xffffffffu, removed);
+    {
+        const int ca = att_new_i >= 0 ? ch : -1;
+        const unsigned ma = __match_any_sync(0xffffffffu, ca);
+        if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&a.att_cnt[b * LSS_N_CHANNELS + ca], (unsigned)__popc(ma));
+        unsigned long long sn = att_new_i >= 0 ? (unsigned long long)(att_new_i < 0 ? 0 : att_new_i) : 0ull;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, s);
+        for (int s = 16; s > 0; s >>= 1) sn += __shfl_xor_sync(0xffffffffu, sn, s);
+        if (lane == 0 && sn) atomicAdd(&a.att_sum[b], sn);
+    }
     if (lane == 0) {
         if (m_att) atomicAdd(&a.counters[2 * b], __popc(m_att));
         if (m_rem) atomicAdd(&a.counters[2 * b + 1], __popc(m_rem));
-        if (diff != 0.0) atomicAdd(&a.stats[4 * b + 3], diff);
     }
 }
 
@@ -486,7 +509,9 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
 // one warp per bin at a time, tiles scanned 32 at a time.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_tile_scan(unsigned *hist, const int32_t *__restrict__ tile_base,
-                                                     int32_t *counts /* or null */, double *stats, const int *counters)
+                                                     int32_t *counts /* or null */, double *stats, const int *counters,
+                                                     const unsigned *att_cnt, const unsigned long long *att_sum,
+                                                     const SensorConst *sensor)
 {
     __shared__ unsigned bin_total[NBINS];
     const int b = blockIdx.x;
@@ -513,7 +538,12 @@ __global__ void __launch_bounds__(1024) k_tile_scan(unsigned *hist, const int32_
         if (counts) counts[b] = (int32_t)run;
         if (stats) {
             const int n_att = counters[2 * b], n_rem = counters[2 * b + 1];
-            const double sum = stats[4 * b + 3];
+            // intensity_diff_sum = sum over attenuated beams of (0.9 * max_intensity - new_i)   (simulation.py:140,170)
+            double sum = 0.0;
+            for (int c = 0; c < LSS_N_CHANNELS; c++)
+                sum += (double)att_cnt[b * LSS_N_CHANNELS + c] * (0.9 * sensor->max_intensity[c]);
+            sum -= (double)att_sum[b];
+            stats[4 * b + 3] = sum;
             stats[4 * b + 0] = (double)n_att;
             stats[4 * b + 1] = (double)n_rem;
             stats[4 * b + 2] = n_att > 0 ? (double)(long long)(sum / (double)n_att) : 0.0;   // int(sum / n), :527-530
@@ -572,7 +602,7 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
     int64_t aug, code_keep, code_all, nocc, hist_keep, hist_all, hist_rows, cloud_off, tile_base, order, thresh, counters,
-        prepass, prepass_bytes, total;
+        counters_bytes, prepass, prepass_bytes, total;
 };
 
 WsLayout ws_layout(int64_t n_total, int n_clouds)
@@ -590,7 +620,9 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     w.tile_base = o;  o = align_up(o + (int64_t)(n_clouds + 1) * 4, 256);
     w.order = o;      o = align_up(o + (int64_t)n_clouds * LSS_N_CHANNELS * 4, 256);
     w.thresh = o;     o = align_up(o + (int64_t)n_clouds * 3 * 8, 256);
-    w.counters = o;   o = align_up(o + (int64_t)n_clouds * 2 * 4, 256);
+    // counters: int[B*2] | unsigned att_cnt[B*64] | unsigned long long att_sum[B]
+    w.counters_bytes = align_up((int64_t)n_clouds * 2 * 4, 8) + (int64_t)n_clouds * LSS_N_CHANNELS * 4 + (int64_t)n_clouds * 8;
+    w.counters = o;   o = align_up(o + w.counters_bytes, 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -649,13 +681,15 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     int32_t *d_order = (int32_t *)(ws + w.order);
     double *d_thresh = (double *)(ws + w.thresh);
     int *d_counters = (int *)(ws + w.counters);
+    unsigned *d_att_cnt = (unsigned *)(ws + w.counters + align_up((int64_t)B * 2 * 4, 8));
+    unsigned long long *d_att_sum = (unsigned long long *)((char *)d_att_cnt + (int64_t)B * LSS_N_CHANNELS * 4);
 
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, s.h_cloud_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, stream));
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_tile_base, h_tile_base.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, stream));
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_order, s.h_order, sizeof(int32_t) * B * LSS_N_CHANNELS, cudaMemcpyHostToDevice, stream));
     if (s.h_thresh_poly)
         LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_thresh, s.h_thresh_poly, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, stream));
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_counters, 0, sizeof(int) * 2 * B, stream));
+    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_counters, 0, w.counters_bytes, stream));
     LSS_CUDA_CHECK(e, cudaMemsetAsync(s.d_out_stats, 0, sizeof(double) * 4 * B, stream));
     if (N == 0 || B == 0) {
         if (B) LSS_CUDA_CHECK(e, cudaMemsetAsync(s.d_out_counts, 0, sizeof(int32_t) * B, stream));
@@ -700,6 +734,8 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.tile_base = d_tile_base;
     a.stats = s.d_out_stats;
     a.counters = d_counters;
+    a.att_cnt = d_att_cnt;
+    a.att_sum = d_att_sum;
     a.status = e->d_status;
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
@@ -708,7 +744,8 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     }
     {
         KernelTimer kt(e, LSS_K_SORT, stream);
-        k_tile_scan<<<B, 1024, 0, stream>>>(d_hist_keep, d_tile_base, s.d_out_counts, s.d_out_stats, d_counters);
+        k_tile_scan<<<B, 1024, 0, stream>>>(d_hist_keep, d_tile_base, s.d_out_counts, s.d_out_stats, d_counters,
+                                            d_att_cnt, d_att_sum, e->d_sensor);
     }
     {
         KernelTimer kt(e, LSS_K_COMPACT, stream);
@@ -717,7 +754,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     }
     if (want_all) {     // un-filtered, channel-sorted debug views (tests): full rows, original index, occluder counts
         KernelTimer kt(e, LSS_K_COMPACT, stream);
-        k_tile_scan<<<B, 1024, 0, stream>>>(d_hist_all, d_tile_base, nullptr, nullptr, nullptr);
+        k_tile_scan<<<B, 1024, 0, stream>>>(d_hist_all, d_tile_base, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         k_scatter<<<dim3(max_tiles, B), TILE, 0, stream>>>(d_aug, d_code_all, d_hist_all, d_off, d_tile_base, s.d_out_full,
                                                            d_nocc_tmp, s.d_out_nocc, s.d_out_perm);
         e->launches++;

@@ -61,7 +61,8 @@ def test_golden_channel_cases(engine, gold_dir):
         r = run_full(engine, tid, rec[f'c{ci}_points'], list(range(64)), theta=rec[f'c{ci}_theta'])
         engine.free_tables(tid)
         assert np.array_equal(r['full'], rec[f'c{ci}_out']), f'case {ci}'
-        assert r['stats'][0, 3] == float(rec[f'c{ci}_sum'])
+        # the reference adds (0.9 * max_intensity - new_i) beam by beam; the device adds exact integer partial sums
+        assert np.isclose(r['stats'][0, 3], float(rec[f'c{ci}_sum']), rtol=1e-12, atol=0)
         assert np.array_equal(r['nocc'], rec[f'c{ci}_nocc'])
 
 
@@ -107,7 +108,7 @@ def test_vs_oracle_cloud(engine, oracle, tables18k):
     n = int(r['counts'][0])
     assert np.array_equal(r['points'][:n], o_aug)
     assert (int(r['stats'][0, 0]), int(r['stats'][0, 1]), int(r['stats'][0, 2])) == o_stats
-    assert r['stats'][0, 3] == oi['intensity_diff_sum']
+    assert np.isclose(r['stats'][0, 3], oi['intensity_diff_sum'], rtol=1e-12, atol=0)
 
     # device-computed theta (correctly rounded float32 of the float64 atan2): the only differences allowed are beams
     # whose azimuth differs by an ulp from the host libm's atan2f -- report and bound the mismatch rate
