@@ -99,7 +99,7 @@ __device__ __forceinline__ double xsi32(float r)
 // ---------------------------------------------------------------------------------------------------------------------
 // per-beam solve
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
+__global__ void __launch_bounds__(SNOW_TPB, 8) k_snowfall(DevArgs a)
 {
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
     __shared__ double s_amp[SNOW_WARPS][POOL];
@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
     // warp's pool; the candidates of all beams of the warp are then evaluated 32 at a time and reduced per beam with a
     // segmented scan (first maximum wins, np.argmax).
     const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
+    const double inv_ctau = 1.0 / ctau;
     // candidate segments of this beam: calls f(k_lo, k_hi, first pulse, last pulse) in ascending sample order
     auto for_each_segment = [&](auto &&f) {
         int j = 0;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                 double v = 0.0;
                 for (int q = j0; q <= j1; q++)
                     if (k >= ks[q] && k < ke[q]) {
-                        const double sn = sin((LSS_PI * (Rk - hr[q])) / ctau);
+                        const double sn = sinpi((Rk - hr[q]) * inv_ctau);
                         v += ha1[q] * (sn * sn);
                     }
                 if (v > best) { best = v; kbest = k; }
@@ -374,7 +375,8 @@ __global__ void __launch_bounds__(SNOW_TPB) k_snowfall(DevArgs a)
                     for (int q = q0; q <= q1; q++) {
                         const int wn = s_win[wid][q];
                         if (k >= (wn & 0xffff) && k < (wn >> 16)) {
-                            const double sn = sin((LSS_PI * (Rk - s_r[wid][q])) / ctau);
+                            // sin(pi (R - r) / (c tau)) of simulation.py:549, as sinpi of the normalised offset
+                            const double sn = sinpi((Rk - s_r[wid][q]) * inv_ctau);
                             v += s_amp[wid][q] * (sn * sn);
                         }
                     }
