@@ -99,7 +99,7 @@ __device__ __forceinline__ double xsi32(float r)
 // ---------------------------------------------------------------------------------------------------------------------
 // per-beam solve
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SNOW_TPB, 8) k_snowfall(DevArgs a)
+__global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs a)
 {
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
     __shared__ double s_amp[SNOW_WARPS][POOL];
@@ -377,22 +377,24 @@ __global__ void __launch_bounds__(SNOW_TPB, 8) k_snowfall(DevArgs a)
                         if (k >= (wn & 0xffff) && k < (wn >> 16)) {
                             // sin(pi (R - r) / (c tau)) of simulation.py:549, as sinpi of the normalised offset
                             const double sn = sinpi((Rk - s_r[wid][q]) * inv_ctau);
-                            v += s_amp[wid][q] * (sn * sn);
+                            v += s_amp[wid][q] * (sn * sn);      // pulses in dict order, like the reference's i[k] +=
                         }
                     }
                 }
-                // segmented inclusive scan over lanes of the same beam: candidates are ordered by (beam, sample)
-                int ok_key = (owner << 16) | k;
-#pragma unroll
-                for (int s = 1; s < 32; s <<= 1) {
-                    const double ov = __shfl_up_sync(0xffffffffu, v, s);
-                    const int okey = __shfl_up_sync(0xffffffffu, ok_key, s);
-                    if (lane >= s && (okey >> 16) == owner && (ov > v || (ov == v && okey < ok_key))) { v = ov; ok_key = okey; }
+                // per-beam argmax over the lanes holding candidates of the same beam: peer groups by beam, then three
+                // integer reductions (non-negative doubles order like their bit patterns): max high word, max low word
+                // among those, min sample index among the exact ties -> the first maximum, like np.argmax
+                const unsigned peers = __match_any_sync(0xffffffffu, owner);
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+                const unsigned vhi = (unsigned)(vb >> 32), vlo = (unsigned)vb;
+                const unsigned mhi = __reduce_max_sync(peers, vhi);
+                const unsigned mlo = __reduce_max_sync(peers, vhi == mhi ? vlo : 0u);
+                const bool is_max = (vhi == mhi) && (vlo == mlo);
+                const unsigned kmin = __reduce_min_sync(peers, is_max ? (unsigned)k : 0xffffffffu);
+                if (owner >= 0 && lane == __ffs(peers) - 1) {
+                    const double vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+                    if (vmax > s_best[wid][owner]) { s_best[wid][owner] = vmax; s_kbest[wid][owner] = (int)kmin; }
                 }
-                k = ok_key & 0xffff;
-                const int nxt = __shfl_down_sync(0xffffffffu, owner, 1);
-                const bool tail = owner >= 0 && (lane == 31 || nxt != owner);
-                if (tail && v > s_best[wid][owner]) { s_best[wid][owner] = v; s_kbest[wid][owner] = k; }
                 __syncwarp();
             }
         }
