@@ -268,17 +268,13 @@ def main():
     # ---- end to end through the public API with host buffers (`e2e`) --------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host_out = torch.empty((N, 5), dtype=torch.float32).pin_memory()
-        host_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-        host_stats = torch.empty((B, 4), dtype=torch.float64).pin_memory()
-        d_in = torch.empty_like(d_pts)
+        host_out = {}
 
         def e2e_step():
-            d_in.copy_(host_pts, non_blocking=True)
-            r = step(d_in)
-            host_out.copy_(r['points'], non_blocking=True)
-            host_counts.copy_(r['counts'], non_blocking=True)
-            host_stats.copy_(r['stats'], non_blocking=True)
+            # public host-to-host API: pinned host batch -> chunked H2D / kernels / D2H pipeline -> pinned host result
+            r = eng.snowfall_batch_host(tid, host_pts, off, orders, DIV_DEG, host_out=host_out, thresh_poly=poly,
+                                        device_prepass=device_prepass, n_chunks=4, n_slots=3)
+            return r
 
         for _ in range(2):
             e2e_step()
@@ -295,7 +291,9 @@ def main():
         dt = float(tt.item())
         e2e = {'value': points_all / dt, 'unit': 'points/s', 'h2d_bytes_per_step': int(N * 20),
                'd2h_bytes_per_step': int(N * 20 + B * 4 + B * 32), 'ms_per_step': dt * 1e3,
-               'timing': 'host wall clock around H2D + augment + D2H, synchronised every step'}
+               'timing': 'host wall clock around SnowfallEngine.snowfall_batch_host (pinned host in -> 4 chunks over 3 '
+                         'streams: H2D, kernels, D2H -> pinned host out), synchronised every step; with N > 1 every rank '
+                         'feeds its own host-side consumer, no gather'}
 
     if rank != 0:
         if world > 1:

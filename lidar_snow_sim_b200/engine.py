@@ -117,7 +117,7 @@ class SnowfallEngine:
     def snowfall_batch(self, table_id, points, cloud_offsets, order, beam_divergence_deg, theta=None,
                        thresh_poly=None, noise_floor=0.7, threshold_filter=True, camera_fov=False,
                        device_prepass=False, assume_sorted=False, want_full=False, want_perm=False, want_nocc=False,
-                       out=None):
+                       out=None, workspace=None):
         """
         Batched augment() on device-resident clouds (enqueued on torch's current stream, no synchronisation).
 
@@ -159,7 +159,11 @@ class SnowfallEngine:
                 out['perm'] = torch.empty((N,), dtype=torch.int32, device=self.device)
             if want_nocc and 'nocc' not in out:
                 out['nocc'] = torch.empty((N,), dtype=torch.int32, device=self.device)
-            ws, need = self._workspace(N, B)
+            if workspace is None:
+                ws, need = self._workspace(N, B)
+            else:
+                ws = workspace
+                assert ws.numel() >= self.lib.lss_snowfall_workspace_bytes(N, B)
             st = self.lib.lss_snowfall_batch(
                 self.h, int(table_id), _ptr(points), _ptr(off), B, _ptr(order), float(beam_divergence_deg),
                 _ptr(theta), _ptr(tp), float(noise_floor), flags, _ptr(out['points']), _ptr(out['counts']),
@@ -168,6 +172,67 @@ class SnowfallEngine:
                 _ptr(ws), int(ws.numel()), self._stream())
         _lib.check(st, self.h)
         return out
+
+    def snowfall_batch_host(self, table_id, host_points, cloud_offsets, order, beam_divergence_deg, host_out=None,
+                            n_chunks=4, n_slots=3, **kw):
+        """
+        Host-to-host batched augment(): `host_points` is a pinned CPU float32 (N, 5) tensor.  The batch is cut into
+        `n_chunks` groups of whole clouds that flow through `n_slots` independent streams (H2D copy, kernels, D2H copy
+        each in stream order), so that the PCIe transfers of one chunk overlap the kernels of another.
+        Returns dict(points, counts, stats) of pinned CPU tensors in the slot-compacted layout; synchronises.
+        """
+        off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
+        B = off.shape[0] - 1
+        N = int(off[-1])
+        assert not host_points.is_cuda and host_points.dtype == torch.float32 and host_points.shape == (N, 5)
+        order = np.ascontiguousarray(order, dtype=np.int32).reshape(B, 64)
+        tp = kw.pop('thresh_poly', None)
+        if tp is not None:
+            tp = np.ascontiguousarray(tp, dtype=np.float64).reshape(B, 3)
+        if host_out is None:
+            host_out = {}
+        if 'points' not in host_out:
+            host_out['points'] = torch.empty((N, 5), dtype=torch.float32).pin_memory()
+            host_out['counts'] = torch.empty((B,), dtype=torch.int32).pin_memory()
+            host_out['stats'] = torch.empty((B, 4), dtype=torch.float64).pin_memory()
+        n_chunks = max(1, min(n_chunks, B))
+        bounds = [round(c * B / n_chunks) for c in range(n_chunks + 1)]
+        max_rows = max(int(off[bounds[c + 1]] - off[bounds[c]]) for c in range(n_chunks))
+        max_b = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
+        key = (max_rows, max_b, n_slots)
+        with torch.cuda.device(self.device):
+            if getattr(self, '_host_slots_key', None) != key:
+                need = self.lib.lss_snowfall_workspace_bytes(max_rows, max_b)
+                self._host_slots = [dict(stream=torch.cuda.Stream(self.device),
+                                         d_in=torch.empty((max_rows, 5), dtype=torch.float32, device=self.device),
+                                         ws=torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device),
+                                         out=dict(points=torch.empty((max_rows, 5), dtype=torch.float32, device=self.device),
+                                                  counts=torch.empty((max_b,), dtype=torch.int32, device=self.device),
+                                                  stats=torch.empty((max_b, 4), dtype=torch.float64, device=self.device)))
+                                    for _ in range(n_slots)]
+                self._host_slots_key = key
+            cur = torch.cuda.current_stream(self.device)
+            for sl in self._host_slots:
+                sl['stream'].wait_stream(cur)
+            for c in range(n_chunks):
+                sl = self._host_slots[c % n_slots]
+                b0, b1 = bounds[c], bounds[c + 1]
+                r0, r1 = int(off[b0]), int(off[b1])
+                nb, nr = b1 - b0, r1 - r0
+                with torch.cuda.stream(sl['stream']):
+                    d_in = sl['d_in'][:nr]
+                    d_in.copy_(host_points[r0:r1], non_blocking=True)
+                    out = dict(points=sl['out']['points'][:nr], counts=sl['out']['counts'][:nb],
+                               stats=sl['out']['stats'][:nb])
+                    self.snowfall_batch(table_id, d_in, off[b0:b1 + 1] - off[b0], order[b0:b1], beam_divergence_deg,
+                                        thresh_poly=None if tp is None else tp[b0:b1], out=out, workspace=sl['ws'], **kw)
+                    host_out['points'][r0:r1].copy_(out['points'], non_blocking=True)
+                    host_out['counts'][b0:b1].copy_(out['counts'], non_blocking=True)
+                    host_out['stats'][b0:b1].copy_(out['stats'], non_blocking=True)
+            for sl in self._host_slots:
+                cur.wait_stream(sl['stream'])
+        self.check()
+        return host_out
 
     def noise_threshold_poly(self, points, cloud_offsets, noise_floor=0.7, plane=None):
         """Device pre-pass only: returns (poly (B,3) float64 tensor in np.polyfit order, plane (B,4) tensor).

@@ -277,3 +277,23 @@ def test_full_size_properties(engine, tables18k):
     print('label fractions', frac)
     assert frac[1] > 0.05 and frac[2] > 0.005
     engine.free_tables(tid)
+
+
+def test_host_pipeline_matches_device(engine, tables18k):
+    """snowfall_batch_host (pinned host in/out, chunked over streams) == snowfall_batch on device-resident input."""
+    B = 6
+    clouds = [synthetic_cloud(seed=300 + b, n_azimuth=256 + 64 * b) for b in range(B)]
+    off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+    orders = np.stack([np.random.default_rng(b).permutation(64) for b in range(B)]).astype(np.int32)
+    host = torch.from_numpy(np.concatenate(clouds)).pin_memory()
+    tid = engine.upload_tables(tables18k)
+    dev = engine.snowfall_batch(tid, host.cuda(), off, orders, DIV, device_prepass=True)
+    engine.check()
+    dev = {k: v.cpu() for k, v in dev.items()}
+    for chunks in (1, 4, 6):
+        got = engine.snowfall_batch_host(tid, host, off, orders, DIV, device_prepass=True, n_chunks=chunks)
+        assert torch.equal(got['counts'], dev['counts']) and torch.equal(got['stats'], dev['stats'])
+        for b in range(B):
+            n = int(dev['counts'][b])
+            assert torch.equal(got['points'][off[b]:off[b] + n], dev['points'][off[b]:off[b] + n])
+    engine.free_tables(tid)
