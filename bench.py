@@ -112,6 +112,23 @@ def make_workload(rank, batch, seed0=0):
     return clouds, np.array(orders, dtype=np.int32)
 
 
+_REF_STATE = None
+
+
+def _ref_init(tables, sensor, clouds, orders, poly, threads):
+    global _REF_STATE
+    from oracle import oracle as orc
+    orc.lib()
+    _REF_STATE = (orc, tables, sensor, clouds, orders, poly, threads)
+
+
+def _ref_one_cloud(k):
+    orc, tables, sensor, clouds, orders, poly, threads = _REF_STATE
+    stats, aug = orc.augment(clouds[k], tables, DIV_DEG, sensor, order=orders[k].tolist(), thresh_poly=poly,
+                             threads=threads, stable_sort=True)
+    return stats
+
+
 def run_reference(args):
     """CPU arm: the oracle port (oracle/, restating tools/snowfall/simulation.py) on all host cores."""
     rank = int(os.environ.get('RANK', '0'))
@@ -128,10 +145,18 @@ def run_reference(args):
     sensor = sensor_arrays()
     poly = np.array(FIXED_POLY)
 
+    # all host cores: clouds are independent -> one worker process per cloud of the step (like the reference's
+    # process_map over channels, simulation.py:490-494), each with its share of threads for the 64 channel tasks
+    import multiprocessing as mp
+    n_workers = max(1, min(cores, clouds_per_step))
+    threads_each = max(1, cores // n_workers)
+    pool = mp.get_context('spawn').Pool(n_workers, initializer=_ref_init,
+                                        initargs=(tables, sensor, clouds, orders, poly if args.host_threshold else None,
+                                                  threads_each))
+    pool.map(_ref_one_cloud, [], chunksize=1)      # workers up before timing
+
     def step():
-        for c, o in zip(clouds, orders):
-            orc.augment(c, tables, DIV_DEG, sensor, order=o.tolist(), thresh_poly=None if not args.host_threshold else poly,
-                        threads=cores, stable_sort=True)
+        pool.map(_ref_one_cloud, range(clouds_per_step), chunksize=1)
 
     for _ in range(args.warmup):
         step()
@@ -141,7 +166,9 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     pts = sum(c.shape[0] for c in clouds)
     value = pts / dt
-    sample = f'{clouds_per_step} clouds of 64x{N_AZIMUTH} per step ({pts} points), full augment() incl. pre-pass'
+    pool.close()
+    sample = (f'{clouds_per_step} clouds of 64x{N_AZIMUTH} per step ({pts} points), full augment() incl. pre-pass; '
+              f'{n_workers} worker processes x {threads_each} threads')
     line = {'impl': 'reference', 'metric': 'augmented LiDAR points/sec', 'value': value, 'unit': 'points/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -168,7 +195,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU)
-    ap.add_argument('--cpu-clouds', type=int, default=2, help='clouds per step of the CPU arm / cpu_baseline sample')
+    ap.add_argument('--cpu-clouds', type=int, default=8, help='clouds per step of the CPU arm / cpu_baseline sample')
     ap.add_argument('--host-threshold', action='store_true',
                     help='skip the device pre-pass and use a fixed threshold polynomial (debug only; reported in config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -324,17 +351,23 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as orc
         from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
+        import multiprocessing as mp
         orc.build()
         cores = os.cpu_count() or 1
         sample = clouds[:args.cpu_clouds]
-        t0 = time.perf_counter()
-        for c, o in zip(sample, orders):
-            orc.augment(c, tables, DIV_DEG, sensor_arrays(), order=o.tolist(),
-                        thresh_poly=None if device_prepass else np.array(FIXED_POLY), threads=cores, stable_sort=True)
-        dt = time.perf_counter() - t0
+        n_workers = max(1, min(cores, len(sample)))
+        threads_each = max(1, cores // n_workers)
+        with mp.get_context('spawn').Pool(n_workers, initializer=_ref_init,
+                                          initargs=(tables, sensor_arrays(), sample, orders,
+                                                    None if device_prepass else np.array(FIXED_POLY), threads_each)) as pool:
+            pool.map(_ref_one_cloud, list(range(min(n_workers, len(sample)))), chunksize=1)     # warm up the workers
+            t0 = time.perf_counter()
+            pool.map(_ref_one_cloud, range(len(sample)), chunksize=1)
+            dt = time.perf_counter() - t0
         cpu = {'value': sum(c.shape[0] for c in sample) / dt, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
                'sample': f'{len(sample)} of the {B} clouds of one step ({sum(c.shape[0] for c in sample)} points), '
-                         f'oracle port (C core + numpy/scipy/sklearn pre-pass), {cores} threads, {dt:.1f} s'}
+                         f'oracle port (C core + numpy/scipy/sklearn pre-pass), {n_workers} processes x '
+                         f'{threads_each} threads, {dt:.1f} s'}
 
     cfg = workload_config(args.gpus)
     cfg['prepass'] = 'device' if device_prepass else 'DEBUG: fixed host-supplied threshold polynomial'

@@ -12,7 +12,6 @@
 #define LSS_PI 3.141592653589793
 #define LSS_TWO_PI 6.283185307179586
 #define LSS_M_EXT 1230            // samples of the range grid R (tools/snowfall/simulation.py:111-116)
-#define LSS_MAX_OCC 48            // per-beam occluder capacity of the in-kernel lists
 #define LSS_ANG_MARGIN 1e-5       // rad; safety margin of the float32 broad phase (0.3 % of the 3 mrad beam)
 
 // Exact per-particle record used by the float64 narrow phase.  All angles in [0, 2 pi).

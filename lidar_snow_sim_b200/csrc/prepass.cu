@@ -239,7 +239,9 @@ __global__ void __launch_bounds__(PP_TPB) k_ransac_trials(PreArgs a)
     const float *win = a.win + a.cloud_off[b] * 3;
     if (threadIdx.x == 0) {
         // three distinct sample indices from a counter-based hash (min_samples = n_features + 1 = 3)
-        unsigned long long s = splitmix64(0x5851F42D4C957F2DULL ^ ((unsigned long long)b << 32) ^ (unsigned)t);
+        // seeded by the cloud's own window size and the trial number -- NOT by the cloud's position in the batch, so a
+        // cloud gets the same plane however it is batched or sharded over GPUs
+        unsigned long long s = splitmix64(0x5851F42D4C957F2DULL ^ ((unsigned long long)(unsigned)K << 32) ^ (unsigned)t);
         int i0 = (int)(s % (unsigned)K);
         s = splitmix64(s);
         int i1 = (int)(s % (unsigned)(K - 1));

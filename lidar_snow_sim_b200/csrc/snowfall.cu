@@ -28,6 +28,9 @@ constexpr int TILE = 1024;                          // rows per scatter tile
 constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
 constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
 constexpr int CCAP = 512;                           // candidate samples a warp evaluates per cooperative batch
+constexpr int FAST_CAP = 16;                        // occluders per beam held by the fast kernel (mean 1-5)
+constexpr int SLOW_CAP = 128;                       // ... by the overflow kernel
+constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel can take per call
 
 struct DevArgs {
     // tables
@@ -61,6 +64,9 @@ struct DevArgs {
     unsigned *att_cnt;           // [B*64] label-1 beams per channel (all of them, simulation.py:170)
     unsigned long long *att_sum; // [B] sum of their new integer intensities
     int *status;
+    // beams with more occluders than the fast kernel's per-beam capacity are deferred to k_snowfall<SLOW_CAP, true>
+    unsigned long long *ovf_list;   // [OVF_LIST_CAP] (cloud << 32 | row)
+    int *ovf_count;
 };
 
 __device__ __forceinline__ void raise_status(int *status, int code) { atomicMax(status, code); }
@@ -99,7 +105,8 @@ __device__ __forceinline__ double xsi32(float r)
 // ---------------------------------------------------------------------------------------------------------------------
 // per-beam solve
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs a)
+template <int CAP, bool SLOW>
+__global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfall(DevArgs a)
 {
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
     __shared__ double s_amp[SNOW_WARPS][POOL];
@@ -109,30 +116,51 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
     __shared__ double s_best[SNOW_WARPS][32];
     __shared__ int s_kbest[SNOW_WARPS][32];
 
-    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // fast kernel: block (x, y) = 128 consecutive rows of cloud y.  Overflow kernel: one listed beam per thread, the
+    // lanes of a warp may belong to different clouds.
+    int b, i, blk0 = 0;
+    bool active;
+    if (SLOW) {
+        const int slot = blockIdx.x * SNOW_TPB + threadIdx.x;
+        const int cnt = min(*a.ovf_count, OVF_LIST_CAP);
+        if (blockIdx.x * SNOW_TPB >= cnt) return;
+        active = slot < cnt;
+        const unsigned long long it = active ? a.ovf_list[slot] : 0ull;
+        b = (int)(it >> 32);
+        i = (int)(it & 0xffffffffu);
+    } else {
+        b = blockIdx.y;
+        blk0 = blockIdx.x * SNOW_TPB;
+        i = blk0 + threadIdx.x;
+    }
     const int64_t beg = a.cloud_off[b];
     const int n = (int)(a.cloud_off[b + 1] - beg);
-    const int blk0 = blockIdx.x * SNOW_TPB;
-    if (blk0 >= n) return;
-    const int i = blk0 + threadIdx.x;
-    const bool active = i < n;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-
+    if (!SLOW) {
+        if (blk0 >= n) return;
+        active = i < n;
+    }
     const int w0 = blk0 + 32 * wid;                                 // first row of this warp
-    const int nf_w = max(0, min(32, n - w0)) * 5;                   // floats of this warp's rows
-    {   // coalesced load of the warp's 32 rows (160 floats); no block-wide barrier anywhere in this kernel
+    const int nf_w = SLOW ? 0 : max(0, min(32, n - w0)) * 5;        // floats of this warp's rows
+    float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
+    if (SLOW) {
+        if (active) {
+            const float *row = a.pts + (beg + i) * 5;
+            px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
+        }
+    } else {
+        // coalesced load of the warp's 32 rows (160 floats); no block-wide barrier anywhere in this kernel
         const float *src = a.pts + (beg + w0) * 5;
 #pragma unroll
         for (int q = 0; q < 5; q++) {
             const int f = q * 32 + lane;
             if (f < nf_w) s_rows[wid][f] = src[f];
         }
-    }
-    __syncwarp();
-    float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
-    if (active) {
-        const float *row = &s_rows[wid][5 * lane];
-        px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
+        __syncwarp();
+        if (active) {
+            const float *row = &s_rows[wid][5 * lane];
+            px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
+        }
     }
     // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
     const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
@@ -145,8 +173,9 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
     const double ctau = 299792458.0 * 1e-8;
 
     // per-beam lists (local memory): hits (a1, a2, range) -> after claiming: pulses (amplitude, range, window)
-    double ha1[LSS_MAX_OCC + 1], ha2[LSS_MAX_OCC], hr[LSS_MAX_OCC + 1];
-    int ks[LSS_MAX_OCC + 1], ke[LSS_MAX_OCC + 1];
+    double ha1[CAP + 1], ha2[CAP], hr[CAP + 1];
+    int ks[CAP + 1], ke[CAP + 1];
+    bool deferred = false;       // fast kernel only: too many occluders, the overflow kernel redoes this beam
     int n_pulses = 0;            // > 0: this beam has a waveform to solve (claiming particles + hard target)
 
     if (active && ch < LSS_N_CHANNELS) {
@@ -189,7 +218,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
                 const bool right_hit = within(right - phi, alpha);
                 const bool left_hit = within(left - phi, alpha);
                 if (!(inside || right_hit || left_hit)) continue;
-                if (L == LSS_MAX_OCC) { overflow = true; break; }
+                if (L == CAP) { overflow = true; break; }
                 const double a1 = right_hit ? right : rp->t_right;   // geometry.py:26-27
                 const double a2 = left_hit ? left : rp->t_left;
                 int j = L - 1;                                   // insertion by range (np.argsort, :416)
@@ -198,7 +227,16 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
                 L++;
             }
         }
-        if (overflow) raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
+        if (overflow) {
+            if (SLOW) {
+                raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
+            } else {
+                const int slot = atomicAdd(a.ovf_count, 1);
+                if (slot < OVF_LIST_CAP) a.ovf_list[slot] = ((unsigned long long)b << 32) | (unsigned)i;
+                else raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
+                deferred = slot < OVF_LIST_CAP;
+            }
+        }
 
         if (L > 0 && !overflow) {
             // ---- compute_occlusion_dict (simulation.py:231-295) ---------------------------------------------------
@@ -213,7 +251,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
                 rb = right - LSS_TWO_PI;
                 for (int j = 0; j < L; j++) if (ha1[j] > ha2[j]) ha1[j] -= LSS_TWO_PI;
             }
-            double ulo[LSS_MAX_OCC], uhi[LSS_MAX_OCC];
+            double ulo[CAP], uhi[CAP];
             int nu = 0;
             double ep_min = fmin(rb, left), ep_max = fmax(rb, left), claimed_total = 0.0;
             int P = 0;          // pulses: claiming particles in range order, then the hard target
@@ -314,7 +352,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
     double best = 0.0;
     int kbest = 0;
     bool coop = n_pulses > 0;
-    if (T_all > CCAP) {          // pathological beam (dozens of overlapping pulses): solve it in this thread
+    if (T_all > CCAP || n_pulses > POOL) {   // pathological beam (dozens of overlapping pulses): solve it in this thread
         coop = false;
         for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
             for (int k = k_lo; k < k_hi; k++) {
@@ -457,9 +495,29 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
                    (depth >= 0.0f);
         }
         removed = !keep;
-        a.code_keep[beg + i] = keep ? (uint8_t)ch : (uint8_t)255;
-        if (a.code_all) a.code_all[beg + i] = (uint8_t)ch;
-        if (a.nocc) a.nocc[beg + i] = n_claim;
+        if (!deferred) {
+            a.code_keep[beg + i] = keep ? (uint8_t)ch : (uint8_t)255;
+            if (a.code_all) a.code_all[beg + i] = (uint8_t)ch;
+            if (a.nocc) a.nocc[beg + i] = n_claim;
+        }
+    }
+    const bool counted = active && !deferred;      // a deferred beam is accounted for by the overflow kernel
+    if (SLOW) {
+        // one unrelated beam per thread: plain stores and per-thread integer atomics
+        if (counted) {
+            float *row = a.aug + (beg + i) * 5;
+            row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
+            const int tile = i / TILE;
+            if (keep) atomicAdd(&a.hist_keep[((size_t)a.tile_base[b] + tile) * NBINS + ch], 1u);
+            if (a.hist_all) atomicAdd(&a.hist_all[((size_t)a.tile_base[b] + tile) * NBINS + ch], 1u);
+            if (att_new_i >= 0) {
+                atomicAdd(&a.att_cnt[b * LSS_N_CHANNELS + ch], 1u);
+                atomicAdd(&a.att_sum[b], (unsigned long long)att_new_i);
+            }
+            if (keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS) atomicAdd(&a.counters[2 * b], 1);
+            if (removed) atomicAdd(&a.counters[2 * b + 1], 1);
+        }
+        return;
     }
     // augmented rows back through shared memory (coalesced store)
     __syncwarp();
@@ -480,24 +538,24 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_snowfall(DevArgs 
     {
         const int tile = blk0 / TILE;
         unsigned *hk = a.hist_keep + ((size_t)a.tile_base[b] + tile) * NBINS;
-        const int ck = (active && keep) ? ch : -1;
+        const int ck = (counted && keep) ? ch : -1;
         const unsigned mk = __match_any_sync(0xffffffffu, ck);
         if (ck >= 0 && lane == __ffs(mk) - 1) atomicAdd(&hk[ck], (unsigned)__popc(mk));
         if (a.hist_all) {
             unsigned *ha = a.hist_all + ((size_t)a.tile_base[b] + tile) * NBINS;
-            const int ca = active ? ch : -1;
+            const int ca = counted ? ch : -1;
             const unsigned ma = __match_any_sync(0xffffffffu, ca);
             if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&ha[ca], (unsigned)__popc(ma));
         }
     }
     // per-cloud statistics: warp-aggregated integer atomics (order independent => bit-reproducible)
-    const unsigned m_att = __ballot_sync(0xffffffffu, keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS);
-    const unsigned m_rem = __ballot_sync(0xffffffffu, removed);
+    const unsigned m_att = __ballot_sync(0xffffffffu, counted && keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS);
+    const unsigned m_rem = __ballot_sync(0xffffffffu, counted && removed);
     {
-        const int ca = att_new_i >= 0 ? ch : -1;
+        const int ca = (counted && att_new_i >= 0) ? ch : -1;
         const unsigned ma = __match_any_sync(0xffffffffu, ca);
         if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&a.att_cnt[b * LSS_N_CHANNELS + ca], (unsigned)__popc(ma));
-        unsigned long long sn = att_new_i >= 0 ? (unsigned long long)(att_new_i < 0 ? 0 : att_new_i) : 0ull;
+        unsigned long long sn = ca >= 0 ? (unsigned long long)att_new_i : 0ull;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) sn += __shfl_xor_sync(0xffffffffu, sn, s);
         if (lane == 0 && sn) atomicAdd(&a.att_sum[b], sn);
@@ -606,7 +664,7 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
     int64_t aug, code_keep, code_all, nocc, hist_keep, hist_all, hist_rows, cloud_off, tile_base, order, thresh, counters,
-        counters_bytes, prepass, prepass_bytes, total;
+        counters_bytes, ovf, prepass, prepass_bytes, total;
 };
 
 WsLayout ws_layout(int64_t n_total, int n_clouds)
@@ -627,6 +685,7 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     // counters: int[B*2] | unsigned att_cnt[B*64] | unsigned long long att_sum[B]
     w.counters_bytes = align_up((int64_t)n_clouds * 2 * 4, 8) + (int64_t)n_clouds * LSS_N_CHANNELS * 4 + (int64_t)n_clouds * 8;
     w.counters = o;   o = align_up(o + w.counters_bytes, 256);
+    w.ovf = o;        o = align_up(o + 256 + (int64_t)OVF_LIST_CAP * 8, 256);      // count (padded) | list
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -741,10 +800,16 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.att_cnt = d_att_cnt;
     a.att_sum = d_att_sum;
     a.status = e->d_status;
+    a.ovf_count = (int *)(ws + w.ovf);
+    a.ovf_list = (unsigned long long *)(ws + w.ovf + 256);
+    LSS_CUDA_CHECK(e, cudaMemsetAsync(a.ovf_count, 0, sizeof(int), stream));
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
         dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
-        k_snowfall<<<grid, SNOW_TPB, 0, stream>>>(a);
+        k_snowfall<FAST_CAP, false><<<grid, SNOW_TPB, 0, stream>>>(a);
+        // beams with more than FAST_CAP occluders (rare): redone with SLOW_CAP; CTAs beyond the list exit at once
+        k_snowfall<SLOW_CAP, true><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
+        e->launches++;
     }
     {
         KernelTimer kt(e, LSS_K_SORT, stream);
