@@ -102,6 +102,30 @@ __device__ __forceinline__ double xsi32(float r)
     return (double)__fadd_rn(__fmul_rn((float)m, r), (float)b);
 }
 
+// Cold or bulky pieces are kept out of line and data-dependent loops are not unrolled: the beam kernel is
+// instruction-fetch sensitive (profiles/: `no_inst` stalls grow with its SASS size), every instruction that is not
+// on the common path costs fetch bandwidth for all resident warps.
+__device__ __noinline__ float azimuth32(float y, float x)
+{
+    // correctly rounded float32 of the float64 atan2 (simulation.py:91 uses a host-dependent float32 np.arctan2)
+    return (float)atan2((double)y, (double)x);
+}
+
+// one waveform sample: sum over the pulses q0..q1 whose window contains k, in dict order (simulation.py:148-149)
+__device__ __noinline__ double waveform_sample(int k, double Rk, int q0, int q1, const double *amp, const double *r,
+                                               const int *ks, const int *ke)
+{
+    const double inv_ctau = 1.0 / (299792458.0 * 1e-8);
+    double v = 0.0;
+#pragma unroll 1
+    for (int q = q0; q <= q1; q++)
+        if (k >= ks[q] && k < ke[q]) {
+            const double sn = sinpi((Rk - r[q]) * inv_ctau);
+            v += amp[q] * (sn * sn);
+        }
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // per-beam solve
 // ---------------------------------------------------------------------------------------------------------------------
@@ -181,7 +205,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
     if (active && ch < LSS_N_CHANNELS) {
         out_l = 0.0f;
         // ---- beam limits (simulation.py:91-101) -------------------------------------------------------------------
-        float th32 = a.theta ? a.theta[beg + i] : (float)atan2((double)py, (double)px);
+        float th32 = a.theta ? a.theta[beg + i] : azimuth32(py, px);
         if (th32 < 0.0f) th32 = __fadd_rn(th32, 6.2831855f);
         const double thd = (double)th32;
         double right = thd - a.half_div, left = thd + a.half_div;
@@ -202,6 +226,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
             const float th_rel = (float)(thm - (bk + 0.5) * a.w);
             const int32_t *bs = a.bucket_start + (int64_t)plane * (a.n_buckets + 1) + bk;
             const int e0 = bs[0], e1 = bs[1];
+#pragma unroll 1
             for (int e = e0; e < e1; e++) {
                 const BroadEntry en = __ldg(&a.entries[e]);
                 if (!(en.x < d32)) break;                       // sorted by range: nothing nearer follows
@@ -222,6 +247,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 const double a1 = right_hit ? right : rp->t_right;   // geometry.py:26-27
                 const double a2 = left_hit ? left : rp->t_left;
                 int j = L - 1;                                   // insertion by range (np.argsort, :416)
+#pragma unroll 1
                 while (j >= 0 && hr[j] > rho) { ha1[j + 1] = ha1[j]; ha2[j + 1] = ha2[j]; hr[j + 1] = hr[j]; j--; }
                 ha1[j + 1] = a1; ha2[j + 1] = a2; hr[j + 1] = rho;
                 L++;
@@ -249,12 +275,14 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
             double rb = right;
             if (straddle) {
                 rb = right - LSS_TWO_PI;
+#pragma unroll 1
                 for (int j = 0; j < L; j++) if (ha1[j] > ha2[j]) ha1[j] -= LSS_TWO_PI;
             }
             double ulo[CAP], uhi[CAP];
             int nu = 0;
             double ep_min = fmin(rb, left), ep_max = fmax(rb, left), claimed_total = 0.0;
             int P = 0;          // pulses: claiming particles in range order, then the hard target
+#pragma unroll 1
             for (int j = 0; j < L; j++) {
                 const double lo = ha1[j], hi = ha2[j];
                 ep_min = fmin(ep_min, fmin(lo, hi));
@@ -262,6 +290,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 if (!(lo < hi)) continue;
                 bool contained = false;
                 double cov = 0.0;
+#pragma unroll 1
                 for (int u = 0; u < nu; u++) {
                     contained |= (ulo[u] <= lo) && (hi <= uhi[u]);
                     const double ov = fmin(hi, uhi[u]) - fmax(lo, ulo[u]);
@@ -272,6 +301,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 claimed_total += claimed;
                 double nlo = lo, nhi = hi;      // merge [lo, hi] into the union (absorb overlapping / touching pieces)
                 int w = 0;
+#pragma unroll 1
                 for (int u = 0; u < nu; u++) {
                     if (ulo[u] <= hi && uhi[u] >= lo) {
                         nlo = fmin(nlo, ulo[u]);
@@ -299,6 +329,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 const double A = (i_orig / beta_0) * beta_0;        // CA_P0 * beta_0 (quirk: every pulse uses it)
                 double *amp = ha1, *rj = hr;                         // reuse the hit arrays
                 bool bad = false;
+#pragma unroll 1
                 for (int j = 0; j < P; j++) {
                     const double r = rj[j];
                     ks[j] = (int)ceil(r * 10);
@@ -355,14 +386,9 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
     if (T_all > CCAP || n_pulses > POOL) {   // pathological beam (dozens of overlapping pulses): solve it in this thread
         coop = false;
         for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
+#pragma unroll 1
             for (int k = k_lo; k < k_hi; k++) {
-                const double Rk = __ldg(&a.R[k]);
-                double v = 0.0;
-                for (int q = j0; q <= j1; q++)
-                    if (k >= ks[q] && k < ke[q]) {
-                        const double sn = sinpi((Rk - hr[q]) * inv_ctau);
-                        v += ha1[q] * (sn * sn);
-                    }
+                const double v = waveform_sample(k, __ldg(&a.R[k]), j0, j1, ha1, hr, ks, ke);
                 if (v > best) { best = v; kbest = k; }
             }
         });
@@ -389,6 +415,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
             if (in_batch) {
                 const int poff = incl - mine;
                 int coff = cincl - myT;
+#pragma unroll 1
                 for (int j = 0; j < mine; j++) {
                     s_amp[wid][poff + j] = ha1[j];
                     s_r[wid][poff + j] = hr[j];
@@ -396,6 +423,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 }
                 for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
                     const unsigned hi_bits = ((unsigned)(poff + j0) << 11) | ((unsigned)(poff + j1) << 18) | ((unsigned)lane << 25);
+#pragma unroll 4
                     for (int k = k_lo; k < k_hi; k++) s_cand[wid][coff++] = (unsigned)k | hi_bits;
                 });
             }
@@ -410,6 +438,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                     owner = desc >> 25;
                     const int q0 = (desc >> 11) & 127u, q1 = (desc >> 18) & 127u;
                     const double Rk = __ldg(&a.R[k]);
+#pragma unroll 1
                     for (int q = q0; q <= q1; q++) {
                         const int wn = s_win[wid][q];
                         if (k >= (wn & 0xffff) && k < (wn >> 16)) {
