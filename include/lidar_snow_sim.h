@@ -184,6 +184,21 @@ LSS_API lss_status lss_dart_throwing_planes(int n_planes, double occupancy_ratio
                                     int distribution, uint64_t *pcg_states, double *h_xyr,
                                     int64_t capacity_per_plane, int64_t *h_counts, int n_threads);
 
+/* Device-resident sampler: the same greedy dart throwing for n_planes planes at once, entirely on the GPU, written to
+ * device memory (feed lss_upload_particles_device).  The acceptance rule and the stop criterion are the reference's;
+ * the random stream is a counter-based generator keyed by (seed, plane, dart) instead of NumPy's PCG64, so parity with
+ * the reference's tables is statistical (use lss_dart_throwing for stream-exact tables).
+ *   n_candidates       darts thrown per plane (must be enough to reach the occupancy: LSS_ERR_WORKSPACE otherwise)
+ *   d_xyr_out          float64[n_planes * capacity_per_plane * 3]: plane p at offset p * capacity_per_plane rows
+ *   d_counts           int32[n_planes] accepted rows per plane
+ *   d_candidates_out   float64[n_planes * n_candidates * 3] or NULL: every dart in throw order (test hook)
+ * Synchronises the stream.                                                                                              */
+LSS_API lss_status lss_sample_particles(lss_engine *e, int n_planes, double occupancy_ratio, double precipitation_rate,
+                                double R_0, int distribution, uint64_t seed, int64_t n_candidates, double *d_xyr_out,
+                                int64_t capacity_per_plane, int32_t *d_counts, double *d_candidates_out,
+                                void *d_workspace, int64_t workspace_bytes, void *stream);
+LSS_API int64_t lss_sample_particles_workspace_bytes(int n_planes, int64_t n_candidates);
+
 /* Optional per-kernel timing for bench.py's roofline: when enabled every kernel launch is bracketed by CUDA events
  * on the launching stream.  lss_kernel_times() (call after synchronising) accumulates and returns, per kernel id
  * 0..n-1 (names via lss_kernel_name), total milliseconds and number of launches; reset != 0 clears the totals.     */

@@ -71,6 +71,9 @@ SIGNATURES = [
                                      _c.POINTER(_c.c_int64)]),
     ('lss_dart_throwing_planes', _c.c_int, [_c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P,
                                             _c.c_int64, _P, _c.c_int]),
+    ('lss_sample_particles', _c.c_int, [_P, _c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_int, _c.c_uint64,
+                                        _c.c_int64, _P, _c.c_int64, _P, _P, _P, _c.c_int64, _P]),
+    ('lss_sample_particles_workspace_bytes', _c.c_int64, [_c.c_int, _c.c_int64]),
     ('lss_set_profiling', _c.c_int, [_P, _c.c_int]),
     ('lss_kernel_times', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int]),
     ('lss_kernel_name', _c.c_char_p, [_c.c_int]),

@@ -97,6 +97,44 @@ class SnowfallEngine:
         self._tables[tid.value] = dict(n_planes=len(off) - 1, max_div=float(max_beam_divergence_rad))
         return tid.value
 
+    def sample_tables_device(self, mode, snowfall_rate, terminal_velocity, seed=1000, R_0=80.0, n_planes=64,
+                             upload=True, max_beam_divergence_rad=DEFAULT_MAX_DIVERGENCE_RAD, n_buckets=2048,
+                             return_candidates=False):
+        """
+        Draw the n_planes snowflake tables of one (snowfall_rate, terminal_velocity) configuration ON THE DEVICE
+        (greedy dart throwing, tools/snowfall/sampling.py:90-194, counter-based random stream) and, with `upload`,
+        build the candidate index from them without a host round trip.  Returns the table id, or with upload=False
+        (xyr (sum N, 3) CUDA float64 tensor, plane_offsets int64 array[, candidates]).
+        """
+        from .snowfall.sampling import compute_occupancy, snowfall_rate_to_rainfall_rate, _expected_capacity, _DIST
+        if mode not in _DIST:
+            raise NotImplementedError('Distribution model unknown.')
+        occ = compute_occupancy(float(snowfall_rate), float(terminal_velocity))
+        rr = float(snowfall_rate_to_rainfall_rate(float(snowfall_rate), float(terminal_velocity)))
+        cap = _expected_capacity(occ, rr, R_0, mode)
+        with torch.cuda.device(self.device):
+            while True:
+                M = cap
+                need = self.lib.lss_sample_particles_workspace_bytes(n_planes, M)
+                ws = torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device)
+                out = torch.empty((n_planes, cap, 3), dtype=torch.float64, device=self.device)
+                counts = torch.empty((n_planes,), dtype=torch.int32, device=self.device)
+                cand = torch.empty((n_planes, M, 3), dtype=torch.float64, device=self.device) if return_candidates else None
+                st = self.lib.lss_sample_particles(self.h, n_planes, occ, rr, float(R_0), _DIST[mode], int(seed), M,
+                                                   _ptr(out), cap, _ptr(counts), _ptr(cand), _ptr(ws), int(ws.numel()),
+                                                   self._stream())
+                if st == _lib.LSS_ERR_WORKSPACE:
+                    cap *= 2
+                    continue
+                _lib.check(st, self.h)
+                break
+            cnt = counts.cpu().numpy().astype(np.int64)
+            off = np.concatenate([[0], np.cumsum(cnt)])
+            xyr = torch.cat([out[p, :cnt[p]] for p in range(n_planes)], dim=0).contiguous()
+        if not upload:
+            return (xyr, off, cand) if return_candidates else (xyr, off)
+        return self.upload_tables_device(xyr, off, max_beam_divergence_rad, n_buckets)
+
     def free_tables(self, table_id):
         _lib.check(self.lib.lss_free_particles(self.h, int(table_id)), self.h)
         self._tables.pop(table_id, None)
