@@ -300,7 +300,7 @@ def main():
         def e2e_step():
             # public host-to-host API: pinned host batch -> chunked H2D / kernels / D2H pipeline -> pinned host result
             r = eng.snowfall_batch_host(tid, host_pts, off, orders, DIV_DEG, host_out=host_out, thresh_poly=poly,
-                                        device_prepass=device_prepass, n_chunks=4, n_slots=3)
+                                        device_prepass=device_prepass, n_chunks=4, n_slots=4)
             return r
 
         for _ in range(2):
@@ -318,7 +318,7 @@ def main():
         dt = float(tt.item())
         e2e = {'value': points_all / dt, 'unit': 'points/s', 'h2d_bytes_per_step': int(N * 20),
                'd2h_bytes_per_step': int(N * 20 + B * 4 + B * 32), 'ms_per_step': dt * 1e3,
-               'timing': 'host wall clock around SnowfallEngine.snowfall_batch_host (pinned host in -> 4 chunks over 3 '
+               'timing': 'host wall clock around SnowfallEngine.snowfall_batch_host (pinned host in -> 4 chunks over 4 '
                          'streams: H2D, kernels, D2H -> pinned host out), synchronised every step; with N > 1 every rank '
                          'feeds its own host-side consumer, no gather'}
 

@@ -212,7 +212,7 @@ class SnowfallEngine:
         return out
 
     def snowfall_batch_host(self, table_id, host_points, cloud_offsets, order, beam_divergence_deg, host_out=None,
-                            n_chunks=4, n_slots=3, **kw):
+                            n_chunks=4, n_slots=4, **kw):
         """
         Host-to-host batched augment(): `host_points` is a pinned CPU float32 (N, 5) tensor.  The batch is cut into
         `n_chunks` groups of whole clouds that flow through `n_slots` independent streams (H2D copy, kernels, D2H copy
