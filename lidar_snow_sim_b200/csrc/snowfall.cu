@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
 #pragma unroll
         for (int q = 0; q < 5; q++) {
             const int f = q * 32 + lane;
-            if (f < nf_w) s_rows[wid][f] = src[f];
+            if (f < nf_w) s_rows[wid][f] = __ldcs(src + f);     // streamed once: do not displace the table index in L2
         }
         __syncwarp();
         if (active) {
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
 #pragma unroll
         for (int q = 0; q < 5; q++) {
             const int f = q * 32 + lane;
-            if (f < nf_w) dst[f] = s_rows[wid][f];
+            if (f < nf_w) dst[f] = s_rows[wid][f];              // read back by k_scatter from L2
         }
     }
     // per-tile channel histograms for the scatter pass (warp-aggregated)
