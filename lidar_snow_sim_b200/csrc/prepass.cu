@@ -387,9 +387,11 @@ __device__ __forceinline__ GroundPt ground_point(const PreArgs &a, const CloudPr
     double c;
     if (a.flat_earth) c = -(z) / (g.d * 1.0);                             // augmentation.py:61-63
     else c = pw / (g.d * cp.nw);                                          // simulation.py:454-455
-    // cos(arccos(c)) == c up to rounding; the reference goes through the angle, and so does the wet-ground kernel
-    g.cosang = cos(acos(c));
-    g.norm_i = (double)r[3] / g.cosang;                                   // augmentation.py:207
+    // The reference forms the angle, arccos(c), and only ever uses its cosine in these regressions
+    // (augmentation.py:207, simulation.py:462): cos(arccos(c)) == c to 1 ulp for |c| <= 1 and NaN beyond, so the two
+    // float64 transcendentals per ground point and pass are skipped (the pre-pass is parity-by-tolerance).
+    g.cosang = (c >= -1.0 && c <= 1.0) ? c : __longlong_as_double(0x7ff8000000000000LL);
+    g.norm_i = g.ground ? (double)r[3] / g.cosang : 0.0;                  // augmentation.py:207
     return g;
 }
 
