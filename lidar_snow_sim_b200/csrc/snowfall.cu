@@ -31,6 +31,11 @@ constexpr int CCAP = 512;                           // candidate samples a warp 
 constexpr int FAST_CAP = 16;                        // occluders per beam held by the fast kernel (mean 1-5)
 constexpr int SLOW_CAP = 128;                       // ... by the overflow kernel
 constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel can take per call
+// kernel modes
+constexpr int MODE_SCAN = 0;      // every beam of the batch: candidate scan; beams without occluders are finished here,
+                                  // the others are pushed to the solve list
+constexpr int MODE_LIST = 1;      // one listed beam per thread (dense: every lane has occluders): scan again, claim,
+                                  // waveform, finish
 
 struct DevArgs {
     // tables
@@ -64,9 +69,14 @@ struct DevArgs {
     unsigned *att_cnt;           // [B*64] label-1 beams per channel (all of them, simulation.py:170)
     unsigned long long *att_sum; // [B] sum of their new integer intensities
     int *status;
-    // beams with more occluders than the fast kernel's per-beam capacity are deferred to k_snowfall<SLOW_CAP, true>
-    unsigned long long *ovf_list;   // [OVF_LIST_CAP] (cloud << 32 | row)
-    int *ovf_count;
+    // work lists (cloud << 32 | row): the scan kernel defers every beam that has occluders to the dense solve kernel,
+    // which in turn defers beams with more than FAST_CAP occluders to the overflow kernel
+    const unsigned long long *list_in;
+    const int *count_in;
+    int cap_in;
+    unsigned long long *list_out;
+    int *count_out;
+    int cap_out;
 };
 
 __device__ __forceinline__ void raise_status(int *status, int code) { atomicMax(status, code); }
@@ -129,9 +139,10 @@ __device__ __noinline__ double waveform_sample(int k, double Rk, int q0, int q1,
 // ---------------------------------------------------------------------------------------------------------------------
 // per-beam solve
 // ---------------------------------------------------------------------------------------------------------------------
-template <int CAP, bool SLOW>
-__global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfall(DevArgs a)
+template <int CAP, int MODE>
+__global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB) k_snowfall(DevArgs a)
 {
+    constexpr bool SLOW = MODE == MODE_LIST;        // listed beams: unrelated rows per lane, scattered I/O
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
     __shared__ double s_amp[SNOW_WARPS][POOL];
     __shared__ double s_r[SNOW_WARPS][POOL];
@@ -147,10 +158,10 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
     bool active;
     if (SLOW) {
         const int slot = blockIdx.x * SNOW_TPB + threadIdx.x;
-        const int cnt = min(*a.ovf_count, OVF_LIST_CAP);
+        const int cnt = min(*a.count_in, a.cap_in);
         if (blockIdx.x * SNOW_TPB >= cnt) return;
         active = slot < cnt;
-        const unsigned long long it = active ? a.ovf_list[slot] : 0ull;
+        const unsigned long long it = active ? a.list_in[slot] : 0ull;
         b = (int)(it >> 32);
         i = (int)(it & 0xffffffffu);
     } else {
@@ -243,6 +254,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 const bool right_hit = within(right - phi, alpha);
                 const bool left_hit = within(left - phi, alpha);
                 if (!(inside || right_hit || left_hit)) continue;
+                if (MODE == MODE_SCAN) { L = 1; break; }           // one occluder is enough to defer the beam
                 if (L == CAP) { overflow = true; break; }
                 const double a1 = right_hit ? right : rp->t_right;   // geometry.py:26-27
                 const double a2 = left_hit ? left : rp->t_left;
@@ -253,18 +265,32 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
                 L++;
             }
         }
+        if (MODE == MODE_SCAN) overflow = false;          // the scan kernel only needs to know whether L > 0
         if (overflow) {
-            if (SLOW) {
+            if (a.list_out == nullptr) {
                 raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
             } else {
-                const int slot = atomicAdd(a.ovf_count, 1);
-                if (slot < OVF_LIST_CAP) a.ovf_list[slot] = ((unsigned long long)b << 32) | (unsigned)i;
+                const int slot = atomicAdd(a.count_out, 1);
+                if (slot < a.cap_out) a.list_out[slot] = ((unsigned long long)b << 32) | (unsigned)i;
                 else raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
-                deferred = slot < OVF_LIST_CAP;
+                deferred = slot < a.cap_out;
+            }
+        }
+        if (MODE == MODE_SCAN) {
+            // defer every beam with occluders (warp-aggregated push: the solve kernel's warps get neighbouring beams)
+            const bool push = L > 0;
+            const unsigned pm = __ballot_sync(__activemask(), push);
+            if (push) {
+                int base = 0;
+                const int leader = __ffs(pm) - 1;
+                if (lane == leader) base = atomicAdd(a.count_out, __popc(pm));
+                base = __shfl_sync(pm, base, leader);
+                a.list_out[base + __popc(pm & ((1u << lane) - 1u))] = ((unsigned long long)b << 32) | (unsigned)i;
+                deferred = true;
             }
         }
 
-        if (L > 0 && !overflow) {
+        if (MODE != MODE_SCAN && L > 0 && !overflow) {
             // ---- compute_occlusion_dict (simulation.py:231-295) ---------------------------------------------------
             // The reference splits the beam into elementary sub-intervals between all sorted end points and lets the
             // particles claim, nearest first, every still-unclaimed piece inside their own interval.  Equivalent
@@ -379,10 +405,10 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
         }
     };
     int T_all = 0;
-    if (n_pulses > 0) for_each_segment([&](int k_lo, int k_hi, int, int) { T_all += k_hi - k_lo; });
+    if (MODE != MODE_SCAN && n_pulses > 0) for_each_segment([&](int k_lo, int k_hi, int, int) { T_all += k_hi - k_lo; });
     double best = 0.0;
     int kbest = 0;
-    bool coop = n_pulses > 0;
+    bool coop = MODE != MODE_SCAN && n_pulses > 0;
     if (T_all > CCAP || n_pulses > POOL) {   // pathological beam (dozens of overlapping pulses): solve it in this thread
         coop = false;
         for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
@@ -395,7 +421,7 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
     }
     s_best[wid][lane] = 0.0;
     s_kbest[wid][lane] = 0;
-    {
+    if (MODE != MODE_SCAN) {
         unsigned remaining = __ballot_sync(0xffffffffu, coop);
         while (remaining) {
             const bool rem = (remaining >> lane) & 1u;
@@ -532,19 +558,26 @@ __global__ void __launch_bounds__(SNOW_TPB, SLOW ? 1 : 1024 / SNOW_TPB) k_snowfa
     }
     const bool counted = active && !deferred;      // a deferred beam is accounted for by the overflow kernel
     if (SLOW) {
-        // one unrelated beam per thread: plain stores and per-thread integer atomics
+        // one unrelated beam per thread: plain stores; integer atomics aggregated over lanes hitting the same counter
         if (counted) {
             float *row = a.aug + (beg + i) * 5;
             row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
-            const int tile = i / TILE;
-            if (keep) atomicAdd(&a.hist_keep[((size_t)a.tile_base[b] + tile) * NBINS + ch], 1u);
-            if (a.hist_all) atomicAdd(&a.hist_all[((size_t)a.tile_base[b] + tile) * NBINS + ch], 1u);
-            if (att_new_i >= 0) {
-                atomicAdd(&a.att_cnt[b * LSS_N_CHANNELS + ch], 1u);
-                atomicAdd(&a.att_sum[b], (unsigned long long)att_new_i);
-            }
-            if (keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS) atomicAdd(&a.counters[2 * b], 1);
-            if (removed) atomicAdd(&a.counters[2 * b + 1], 1);
+        }
+        auto agg_add = [&](bool on, int key, unsigned *base_ptr) {          // base_ptr[key] += #lanes with this key
+            const unsigned m = __match_any_sync(0xffffffffu, on ? key : -1);
+            if (on && lane == __ffs(m) - 1) atomicAdd(base_ptr + key, (unsigned)__popc(m));
+        };
+        const int hrow = counted ? (a.tile_base[b] + i / TILE) * NBINS + ch : 0;
+        agg_add(counted && keep, hrow, a.hist_keep);
+        if (a.hist_all) agg_add(counted, hrow, a.hist_all);
+        agg_add(counted && att_new_i >= 0, b * LSS_N_CHANNELS + (ch < LSS_N_CHANNELS ? ch : 0), a.att_cnt);
+        agg_add(counted && keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS, 2 * b, (unsigned *)a.counters);
+        agg_add(counted && removed, 2 * b + 1, (unsigned *)a.counters);
+        {
+            const bool on = counted && att_new_i >= 0;
+            const unsigned m = __match_any_sync(0xffffffffu, on ? b : -1);
+            const unsigned sum = __reduce_add_sync(m, on ? (unsigned)att_new_i : 0u);
+            if (on && lane == __ffs(m) - 1) atomicAdd(&a.att_sum[b], (unsigned long long)sum);
         }
         return;
     }
@@ -714,7 +747,8 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     // counters: int[B*2] | unsigned att_cnt[B*64] | unsigned long long att_sum[B]
     w.counters_bytes = align_up((int64_t)n_clouds * 2 * 4, 8) + (int64_t)n_clouds * LSS_N_CHANNELS * 4 + (int64_t)n_clouds * 8;
     w.counters = o;   o = align_up(o + w.counters_bytes, 256);
-    w.ovf = o;        o = align_up(o + 256 + (int64_t)OVF_LIST_CAP * 8, 256);      // count (padded) | list
+    // counts (padded) | overflow list | solve list (every beam may have occluders)
+    w.ovf = o;        o = align_up(o + 256 + (int64_t)OVF_LIST_CAP * 8 + n_total * 8, 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -829,16 +863,26 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.att_cnt = d_att_cnt;
     a.att_sum = d_att_sum;
     a.status = e->d_status;
-    a.ovf_count = (int *)(ws + w.ovf);
-    a.ovf_list = (unsigned long long *)(ws + w.ovf + 256);
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(a.ovf_count, 0, sizeof(int), stream));
+    int *d_counts2 = (int *)(ws + w.ovf);                                   // [0] solve list, [1] overflow list
+    unsigned long long *d_ovf_list = (unsigned long long *)(ws + w.ovf + 256);
+    unsigned long long *d_solve_list = d_ovf_list + OVF_LIST_CAP;
+    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_counts2, 0, 2 * sizeof(int), stream));
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
+        // 1. scan: all beams; the ones without occluders are finished, the others go to the solve list
+        a.list_in = nullptr; a.count_in = nullptr; a.cap_in = 0;
+        a.list_out = d_solve_list; a.count_out = d_counts2; a.cap_out = (int)std::min<int64_t>(N, 0x7fffffff);
         dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
-        k_snowfall<FAST_CAP, false><<<grid, SNOW_TPB, 0, stream>>>(a);
-        // beams with more than FAST_CAP occluders (rare): redone with SLOW_CAP; CTAs beyond the list exit at once
-        k_snowfall<SLOW_CAP, true><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
-        e->launches++;
+        k_snowfall<FAST_CAP, MODE_SCAN><<<grid, SNOW_TPB, 0, stream>>>(a);
+        // 2. solve: the listed beams, densely packed (every lane has occluders); CTAs beyond the list exit at once
+        a.list_in = d_solve_list; a.count_in = d_counts2; a.cap_in = a.cap_out;
+        a.list_out = d_ovf_list; a.count_out = d_counts2 + 1; a.cap_out = OVF_LIST_CAP;
+        k_snowfall<FAST_CAP, MODE_LIST><<<(unsigned)((N + SNOW_TPB - 1) / SNOW_TPB), SNOW_TPB, 0, stream>>>(a);
+        // 3. overflow: beams with more than FAST_CAP occluders (rare), redone with SLOW_CAP
+        a.list_in = d_ovf_list; a.count_in = d_counts2 + 1; a.cap_in = OVF_LIST_CAP;
+        a.list_out = nullptr; a.count_out = nullptr; a.cap_out = 0;
+        k_snowfall<SLOW_CAP, MODE_LIST><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
+        e->launches += 2;
     }
     {
         KernelTimer kt(e, LSS_K_SORT, stream);
