@@ -28,7 +28,7 @@ constexpr int TILE = 1024;                          // rows per scatter tile
 constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
 constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
 constexpr int CCAP = 512;                           // candidate samples a warp evaluates per cooperative batch
-constexpr int FAST_CAP = 16;                        // occluders per beam held by the fast kernel (mean 1-5)
+constexpr int FAST_CAP = 24;                        // occluders per beam held by the fast kernel (mean 1-5)
 constexpr int SLOW_CAP = 128;                       // ... by the overflow kernel
 constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel can take per call
 // kernel modes

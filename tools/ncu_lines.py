@@ -7,7 +7,12 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'],
+extra = []
+for a in sys.argv[3:]:
+    if a.startswith('--launch='):                      # which captured launch of the report (0-based)
+        extra = ['--launch-skip', a.split('=')[1], '--launch-count', '1']
+sys.argv = [a for a in sys.argv if not a.startswith('--launch=')]
+out = subprocess.run(['ncu', '-i', rep] + extra + ['--page', 'source', '--print-source', 'cuda,sass', '--csv'],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = None
