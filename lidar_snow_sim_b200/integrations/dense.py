@@ -1,0 +1,101 @@
+"""
+On-the-fly SNOW / WET_SURFACE augmentation for the reference's training data path.
+
+Mirrors the block of `DenseDataset.__getitem__` that applies the two augmentations
+(lib/OpenPCDet/pcdet/datasets/dense/dense_dataset.py:749-837): same config keys and strings
+(`SNOW: '<sampling>_<mode>_<chance>'`, `WET_SURFACE: '<chance>[_norm]'`, `COUPLED`), same use of NumPy's global RNG for
+the coin flips, same water-height distributions, same exception swallowing around the wet-ground call.
+
+The one difference is the point of the engine: SNOW no longer READS files pre-computed by tools/snowfall/precompute.py
+(`<root>/snowfall_simulation/<mode>/<lidar_folder>_rainrate_<int>/<id>.bin`, :778-783) -- it computes the same thing on
+the GPU when the sample is requested: camera-FOV filter, augment() with the (snowfall_rate, terminal_velocity) pair
+whose rain rate the reference would have picked, FOV filter again (precompute.py:96-104).  Snowflake tables are drawn
+on the device once per (mode, pair) and cached.
+
+    aug = OnTheFlyWeather(dataset_cfg, rainfall_rates=[...])        # in DenseDataset.__init__
+    points = aug(points, training=self.training)                    # replaces dense_dataset.py:749-837
+"""
+import numpy as np
+
+from ..engine import default_engine
+from ..snowfall.precompute import SNOWFALL_RATES, TERMINAL_VELOCITIES, get_fov_flag
+from ..snowfall.sampling import snowfall_rate_to_rainfall_rate
+from ..snowfall.simulation import augment
+from ..wet_ground.augmentation import ground_water_augmentation
+
+_CHANCES = {'8in9': [1, 1, 1, 1, 1, 1, 1, 1, 0], '4in5': [1, 1, 1, 1, 0], '1in2': [1, 0], '1in4': [1, 0, 0, 0],
+            '1in10': [1, 0, 0, 0, 0, 0, 0, 0, 0, 0]}                     # dense_dataset.py:761-770
+
+
+class OnTheFlyWeather:
+    def __init__(self, dataset_cfg, rainfall_rates=None, engine=None, table_seed=42):
+        self.cfg = dataset_cfg
+        self.engine = engine
+        self.table_seed = table_seed
+        # the integer rain rates the pre-computed folders are named after (precompute.py:57,88-89)
+        self.pairs = {}
+        for rs, tv in zip(SNOWFALL_RATES, TERMINAL_VELOCITIES):
+            self.pairs[int(snowfall_rate_to_rainfall_rate(rs, tv))] = (rs, tv)
+        self.rainfall_rates = list(rainfall_rates) if rainfall_rates is not None else sorted(self.pairs)
+        self._tables = {}
+
+    def _engine(self):
+        if self.engine is None:
+            self.engine = default_engine()
+        return self.engine
+
+    def _table(self, mode, rainfall_rate):
+        key = (mode, rainfall_rate)
+        if key not in self._tables:
+            if rainfall_rate not in self.pairs:
+                raise FileNotFoundError(f'no (snowfall_rate, terminal_velocity) pair with rain rate {rainfall_rate}')
+            rs, tv = self.pairs[rainfall_rate]
+            self._tables[key] = self._engine().sample_tables_device(mode, rs, tv, seed=self.table_seed)
+        return self._tables[key]
+
+    def __call__(self, points, training=True):
+        cfg = self.cfg
+        snowfall_augmentation_applied = False
+        if training and 'SNOW' in cfg:
+            sampling, mode, chance = cfg['SNOW'].split('_')[:3]
+            choices = _CHANCES.get(chance, [0])
+            if np.random.choice(choices):
+                rainfall_rate = 0
+                if sampling == 'uniform':
+                    rainfall_rate = int(np.random.choice(self.rainfall_rates))
+                try:
+                    tid = self._table(mode, rainfall_rate)
+                    pc = np.ascontiguousarray(points[:, :5], dtype=np.float32)
+                    pc = pc[get_fov_flag(pc[:, 0:3])]                                  # precompute.py:96-99
+                    _, points = augment(pc, '', float(np.degrees(3e-3)), engine=self._engine(), tables=tid)
+                    snowfall_augmentation_applied = True
+                except FileNotFoundError as exc:                                       # dense_dataset.py:784-786
+                    print(f'\\n{exc}')
+        if training and 'WET_SURFACE' in cfg:
+            method = cfg['WET_SURFACE']
+            choices = [0]
+            if '1in2' in method:
+                choices = [0, 1]
+            elif '1in4' in method:
+                choices = [0, 0, 0, 1]
+            elif '1in10' in method:
+                choices = [0, 0, 0, 0, 0, 0, 0, 0, 0, 1]
+            apply_coupled = 'COUPLED' in cfg and snowfall_augmentation_applied
+            if 'COUPLED' in cfg:
+                choices = [0]
+            if np.random.choice(choices) or apply_coupled:
+                if 'norm' in method:
+                    from scipy import stats
+                    lower, upper, mu, sigma = 0.05, 0.5, 0.2, 0.1
+                    water_height = stats.truncnorm((lower - mu) / sigma, (upper - mu) / sigma, loc=mu, scale=sigma).rvs(1)
+                else:
+                    elements = np.linspace(0.1, 1.2, 12)
+                    probabilities = 5 * np.ones_like(elements)
+                    probabilities[0], probabilities[1], probabilities[2] = 15, 25, 15
+                    water_height = np.random.choice(elements, 1, p=probabilities / 100)
+                try:
+                    points = ground_water_augmentation(points, water_height=float(np.asarray(water_height).reshape(-1)[0]),
+                                                       debug=False, engine=self._engine())
+                except (TypeError, ValueError):                                        # dense_dataset.py:834-837
+                    pass
+        return points
