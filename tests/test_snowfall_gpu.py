@@ -297,3 +297,23 @@ def test_host_pipeline_matches_device(engine, tables18k):
             n = int(dev['counts'][b])
             assert torch.equal(got['points'][off[b]:off[b] + n], dev['points'][off[b]:off[b] + n])
     engine.free_tables(tid)
+
+
+def test_degenerate_rows(engine, oracle, tables18k):
+    """Rows at the origin, NaN coordinates, zero / negative intensity: same answer as the oracle, no crash."""
+    pc = synthetic_cloud(seed=41, n_azimuth=64)
+    pc[3, :3] = 0.0                      # at the sensor: range 0, no particle is nearer
+    pc[7, 0] = np.nan
+    pc[11, 1] = np.nan
+    pc[13, 3] = 0.0
+    pc[17, 3] = -5.0
+    pc[19, :3] = [1e-3, -1e-3, 2e-3]
+    order = list(range(64))
+    aug, s, nocc, theta = oracle.snow_cloud(pc, tables18k, order, sensor_arrays(), DIV)
+    aug[:, 3] = np.round(aug[:, 3])
+    tid = engine.upload_tables(tables18k)
+    r = run_full(engine, tid, pc, order, theta=theta)
+    got, want = r['full'], aug
+    same = np.isnan(want) & np.isnan(got) | (want == got)
+    assert same.all()
+    engine.free_tables(tid)
