@@ -51,7 +51,8 @@ typedef enum {
 #define LSS_FLAG_CAMERA_FOV 0x2u         /* apply the camera field-of-view filter (simulation.py:532-540) */
 #define LSS_FLAG_DEVICE_PREPASS 0x4u     /* compute ground plane + noise-threshold polynomial on the device
                                             (simulation.py:449-467) instead of taking h_thresh_poly */
-#define LSS_FLAG_ASSUME_SORTED 0x8u      /* input clouds are already grouped by channel (skips simulation.py:447) */
+#define LSS_FLAG_ASSUME_SORTED 0x8u      /* accepted for compatibility, no effect: the channel sort (simulation.py:447) is
+                                            fused into the final scatter pass and costs nothing extra */
 
 #define LSS_N_CHANNELS 64
 #define LSS_POINT_STRIDE 5
@@ -109,7 +110,7 @@ LSS_API lss_status lss_table_info(lss_engine *e, int table_id, int64_t *n_partic
  *                                         (required with LSS_FLAG_THRESHOLD_FILTER unless LSS_FLAG_DEVICE_PREPASS)
  *   noise_floor                           simulation.py:428 (used by the device pre-pass only)
  *   flags                                 LSS_FLAG_*
- *   d_out_points     float32[n_total*5]   augmented rows (x, y, z, intensity, label), channel-sorted, cloud b
+ *   d_out_points     float32[n_total*5]   augmented rows (x, y, z, intensity, label), sorted by channel (stable), cloud b
  *                                         compacted to the front of its own slot: rows h_cloud_offsets[b] ..
  *                                         h_cloud_offsets[b] + count[b]; rows behind that are unspecified
  *   d_out_counts     int32[n_clouds]      rows kept per cloud
