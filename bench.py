@@ -140,7 +140,11 @@ def run_reference(args):
     orc.build()
     cores = os.cpu_count() or 1
     tables = sample_table_set(MODE, SNOWFALL_RATE, TERMINAL_VELOCITY, seed=1000)
-    clouds_per_step = args.cpu_clouds
+    # bounded sample per step so that `--steps K --warmup W` ends within a few minutes whatever K the driver passes
+    # (one cloud costs ~3-6 core-seconds of the pre-pass + ~20 core-seconds of channel work)
+    total_steps = args.steps + args.warmup
+    clouds_per_step = args.cpu_clouds if args.cpu_clouds > 0 else (8 if total_steps <= 6 else 4 if total_steps <= 14
+                                                                    else 2 if total_steps <= 30 else 1)
     clouds, orders = make_workload(0, clouds_per_step)
     sensor = sensor_arrays()
     poly = np.array(FIXED_POLY)
@@ -195,7 +199,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU)
-    ap.add_argument('--cpu-clouds', type=int, default=8, help='clouds per step of the CPU arm / cpu_baseline sample')
+    ap.add_argument('--cpu-clouds', type=int, default=0, help='clouds per step of the CPU arm / cpu_baseline sample')
     ap.add_argument('--host-threshold', action='store_true',
                     help='skip the device pre-pass and use a fixed threshold polynomial (debug only; reported in config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -356,7 +360,7 @@ def main():
         import multiprocessing as mp
         orc.build()
         cores = os.cpu_count() or 1
-        sample = clouds[:args.cpu_clouds]
+        sample = clouds[:(args.cpu_clouds if args.cpu_clouds > 0 else 8)]
         n_workers = max(1, min(cores, len(sample)))
         threads_each = max(1, cores // n_workers)
         with mp.get_context('spawn').Pool(n_workers, initializer=_ref_init,
