@@ -54,7 +54,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler runs from
+    before the warm-up (nvidia-smi needs ~0.2 s to start); samples are stamped on arrival and the ones that fall inside
+    the timed window are reported (the window is tens of ms: if none falls inside, the nearest ones are used and
+    `window` says so)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -63,11 +66,12 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.gpu_index = gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          '-lms', '20', '-i', str(self.gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -76,20 +80,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(',')])
+            self.rows.append((time.perf_counter(), [t.strip() for t in line.split(',')]))
+
+    def window_begin(self):
+        self.t0 = time.perf_counter()
+
+    def window_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if self.t0 is not None and self.t0 - 0.02 <= t <= self.t1 + 0.03]
+        window = 'inside the timed region'
+        if not rows and self.rows:
+            mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
+            rows = [r for (t, r) in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            window = 'nearest samples (timed region shorter than the sampling period)'
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -99,7 +115,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 def make_workload(rank, batch, seed0=0):
@@ -285,6 +301,8 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput (`value`) ------------------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for k in range(args.warmup):
         step(k)
     drain()
@@ -292,9 +310,8 @@ def main():
     eng.set_profiling(True)
     eng.kernel_times(reset=True)
     launches0 = eng.launch_count()
-    clocks = ClockSampler(local_rank)
     sync_all()
-    clocks.start()
+    clocks.window_begin()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -303,6 +320,7 @@ def main():
     drain()                                                 # the last gathers are inside the timed region
     e1.record()
     sync_all()
+    clocks.window_end()
     clk = clocks.stop()
     eng.check()
     total_ms = float(e0.elapsed_time(e1))
