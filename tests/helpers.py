@@ -34,3 +34,16 @@ def augment_case(g):
     for k in (0, 63):
         assert sha(tables[k]) == str(g['table_sha'][k])
     return pc, tables
+
+
+def augment_full_case(g):
+    """BASELINE.json configs[0]: full-size STF-shaped cloud + dart-throwing tables (1.0 mm/h, 1.6 m/s), from seeds."""
+    from lidar_snow_sim_b200.snowfall.sampling import sample_table_set
+    pc = synthetic_cloud(seed=int(g['seed']), n_azimuth=int(g['n_azimuth']), drop=float(g['drop']))
+    assert sha(pc) == str(g['cloud_sha']), 'synthetic cloud changed: regenerate tests/golden'
+    tables = sample_table_set('gunn', 1.0, 1.6, seed=1000)
+    assert [t.shape[0] for t in tables] == g['table_counts'].tolist()
+    assert [sha(t) for t in tables] == [str(v) for v in g['table_sha']], 'sampler output changed (libm?): regenerate'
+    theta_cr = np.arctan2(pc[:, 1].astype(np.float64), pc[:, 0].astype(np.float64)).astype(np.float32)
+    theta = (theta_cr.view(np.int32) + g['theta_ulp'].astype(np.int32)).view(np.float32)     # the reference host's bits
+    return pc, tables, theta

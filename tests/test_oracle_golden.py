@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import DIV, canon, channel_case, augment_case, sha
+from helpers import DIV, canon, channel_case, augment_case, augment_full_case, sha
 from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
 from lidar_snow_sim_b200.calib.dense_camera import STF_HDL64_CAMERA
 from lidar_snow_sim_b200.snowfall import sampling as prod_sampling
@@ -79,6 +79,19 @@ def test_augment(oracle, gold_dir, name):
     assert stats == tuple(int(v) for v in g['stats'])
     assert np.array_equal(canon(aug), g['out'])
     assert np.allclose(internals['thresh_poly'], g['thresh_poly'], rtol=1e-12, atol=0)
+
+
+def test_augment_full_size(oracle, gold_dir):
+    """BASELINE.json configs[0]: one STF-shaped 64 x 2048 cloud, real dart-throwing tables, against the reference's own
+    output (stored as stats + SHA-256 of the canonically ordered rows)."""
+    g = np.load(os.path.join(gold_dir, 'augment_full.npz'))
+    pc, tables, theta = augment_full_case(g)
+    idx = pc[:, 4].argsort(kind='stable')
+    stats, aug = oracle.augment(pc, tables, DIV, sensor_arrays(), order=g['order'].tolist(), thresh_poly=g['thresh_poly'],
+                                theta_sorted=theta[idx], stable_sort=True)
+    assert stats == tuple(int(v) for v in g['stats'])
+    assert aug.shape == tuple(g['out_shape']) and sha(canon(aug)) == str(g['out_sha'])
+    assert [(aug[:, 4] == l).sum() for l in (0, 1, 2)] == g['label_counts'].tolist()
 
 
 def test_wet_ground(oracle, gold_dir):

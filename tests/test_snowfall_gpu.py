@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import DIV, canon, channel_case, augment_case
+from helpers import DIV, canon, channel_case, augment_case, augment_full_case, sha
 from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
 from lidar_snow_sim_b200.synthetic import synthetic_cloud, synthetic_particles
 
@@ -77,6 +77,22 @@ def test_golden_augment_api(engine, gold_dir, name):
     assert stats == tuple(int(v) for v in g['stats'])
     assert aug.dtype == np.float32
     assert np.array_equal(canon(aug), g['out'])
+
+
+def test_golden_augment_full_size(engine, gold_dir):
+    """BASELINE.json configs[0] end to end against the reference's own output (stats + SHA-256 of the rows)."""
+    from lidar_snow_sim_b200.snowfall.simulation import augment
+    g = np.load(os.path.join(gold_dir, 'augment_full.npz'))
+    pc, tables, theta = augment_full_case(g)
+    stats, aug = augment(pc, 'unused', DIV, only_camera_fov=False, engine=engine, tables=tables,
+                         order=g['order'].tolist(), thresh_poly=g['thresh_poly'], theta=theta)
+    assert stats == tuple(int(v) for v in g['stats'])
+    assert aug.shape == tuple(g['out_shape']) and sha(canon(aug)) == str(g['out_sha'])
+    # device pre-pass instead of the reference's RANSAC draw / argpartition pick: statistically the same cloud
+    stats2, aug2 = augment(pc, 'unused', DIV, only_camera_fov=False, engine=engine, tables=tables,
+                           order=g['order'].tolist(), theta=theta)
+    print('reference stats', stats, 'device pre-pass stats', stats2)
+    assert abs(aug2.shape[0] - aug.shape[0]) < 0.05 * aug.shape[0]
 
 
 # ----------------------------------------------------------------------------------------------------------------------

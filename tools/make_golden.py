@@ -206,6 +206,59 @@ def main():
                             thresh_poly=cap['poly'], theta=theta_orig, stats=np.array(stats, dtype=np.int64),
                             out=canon(aug))
 
+    # ---------------------------------------------------------------- FULL-SIZE augment: 64 x 2048 cloud, dart-throwing tables
+    # (BASELINE.json configs[0]).  Only hashes / small arrays are stored: the cloud and the tables are regenerated from
+    # seeds, the host's float32 arctan2 bits are stored as the ulp offset from the correctly rounded value.
+    from lidar_snow_sim_b200.snowfall.sampling import sample_table_set
+    pc = synthetic_cloud(seed=0, n_azimuth=2048, drop=0.08)
+    tables = sample_table_set('gunn', 1.0, 1.6, seed=1000)
+    root = tempfile.mkdtemp()
+    write_tables(root, 'g', tables)
+    cap = {}
+    orig_cp = ns.sim.calculate_plane
+    orig_polyfit = np.polyfit
+
+    def cp3(p):
+        w, h = orig_cp(p)
+        cap['plane'] = (np.asarray(w, dtype=np.float64), float(h))
+        return w, h
+
+    def pf3(x, y, deg, *a, **k):
+        r = orig_polyfit(x, y, deg, *a, **k)
+        cap['poly'] = np.asarray(r, dtype=np.float64)
+        return r
+
+    ns.sim.calculate_plane = cp3
+    np.polyfit = pf3
+    try:
+        random.seed(7)
+        np.random.seed(7)
+        stats, aug = ns.sim.augment(pc, 'g', DIV, shuffle=True, show_progressbar=True, only_camera_fov=False, root_path=root)
+    finally:
+        ns.sim.calculate_plane = orig_cp
+        np.polyfit = orig_polyfit
+    random.seed(7)
+    order = list(range(64))
+    random.shuffle(order)
+    theta = np.arctan2(pc[:, 1], pc[:, 0])
+    theta_cr = np.arctan2(pc[:, 1].astype(np.float64), pc[:, 0].astype(np.float64)).astype(np.float32)
+    ulp = (theta.view(np.int32).astype(np.int64) - theta_cr.view(np.int32).astype(np.int64))
+    assert np.abs(ulp).max() < 100
+    idx = pc[:, 4].argsort(kind='stable')
+    o_stats, o_aug = orc.augment(pc, tables, DIV, sensor, order=order, thresh_poly=cap['poly'], theta_sorted=theta[idx],
+                                 stable_sort=True)
+    stats = tuple(int(v) for v in stats)
+    good = (stats == o_stats) and aug.shape == o_aug.shape and np.array_equal(canon(aug), canon(o_aug))
+    print(f'augment_full: oracle==reference: {good} stats {stats} out {aug.shape} labels',
+          [(aug[:, 4] == l).sum() for l in (0, 1, 2)])
+    ok &= good
+    np.savez_compressed(os.path.join(GOLD, 'augment_full.npz'), seed=0, n_azimuth=2048, drop=0.08, cloud_sha=sha(pc),
+                        table_sha=np.array([sha(t) for t in tables]), table_counts=np.array([t.shape[0] for t in tables]),
+                        order=np.array(order, dtype=np.int32), plane_w=cap['plane'][0], plane_h=cap['plane'][1],
+                        thresh_poly=cap['poly'], theta_ulp=ulp.astype(np.int8), stats=np.array(stats, dtype=np.int64),
+                        out_sha=sha(canon(aug)), out_shape=np.array(aug.shape),
+                        label_counts=np.array([(aug[:, 4] == l).sum() for l in (0, 1, 2)]))
+
     # ---------------------------------------------------------------- wet ground (wet_ground/augmentation.py:25-161)
     pc = synthetic_cloud(seed=3, n_azimuth=256)
     cap = {}
