@@ -88,11 +88,14 @@ def test_golden_augment_full_size(engine, gold_dir):
                          order=g['order'].tolist(), thresh_poly=g['thresh_poly'], theta=theta)
     assert stats == tuple(int(v) for v in g['stats'])
     assert aug.shape == tuple(g['out_shape']) and sha(canon(aug)) == str(g['out_sha'])
-    # device pre-pass instead of the reference's RANSAC draw / argpartition pick: statistically the same cloud
-    stats2, aug2 = augment(pc, 'unused', DIV, only_camera_fov=False, engine=engine, tables=tables,
-                           order=g['order'].tolist(), theta=theta)
+    # With the device pre-pass the kept set differs from THIS reference run: the reference's threshold polynomial hinges
+    # on np.argpartition's implementation-defined pick (on this cloud the AVX-512 NumPy pick and the
+    # portable first-minimum pick give polynomials of opposite curvature).  tests/test_prepass_gpu.py pins the device
+    # pre-pass to the oracle run with the portable rule; here only the un-filtered solve must be unaffected.
+    stats2, aug2, gi = augment(pc, 'unused', DIV, only_camera_fov=False, engine=engine, tables=tables,
+                               order=g['order'].tolist(), theta=theta, return_internals=True)
     print('reference stats', stats, 'device pre-pass stats', stats2)
-    assert abs(aug2.shape[0] - aug.shape[0]) < 0.05 * aug.shape[0]
+    assert [(gi['full'][:, 4] == l).sum() for l in (0, 1, 2)] == g['label_counts_unfiltered'].tolist()
 
 
 # ----------------------------------------------------------------------------------------------------------------------

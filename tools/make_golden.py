@@ -245,8 +245,8 @@ def main():
     ulp = (theta.view(np.int32).astype(np.int64) - theta_cr.view(np.int32).astype(np.int64))
     assert np.abs(ulp).max() < 100
     idx = pc[:, 4].argsort(kind='stable')
-    o_stats, o_aug = orc.augment(pc, tables, DIV, sensor, order=order, thresh_poly=cap['poly'], theta_sorted=theta[idx],
-                                 stable_sort=True)
+    o_stats, o_aug, o_int = orc.augment(pc, tables, DIV, sensor, order=order, thresh_poly=cap['poly'],
+                                        theta_sorted=theta[idx], stable_sort=True, return_internals=True)
     stats = tuple(int(v) for v in stats)
     good = (stats == o_stats) and aug.shape == o_aug.shape and np.array_equal(canon(aug), canon(o_aug))
     print(f'augment_full: oracle==reference: {good} stats {stats} out {aug.shape} labels',
@@ -257,7 +257,8 @@ def main():
                         order=np.array(order, dtype=np.int32), plane_w=cap['plane'][0], plane_h=cap['plane'][1],
                         thresh_poly=cap['poly'], theta_ulp=ulp.astype(np.int8), stats=np.array(stats, dtype=np.int64),
                         out_sha=sha(canon(aug)), out_shape=np.array(aug.shape),
-                        label_counts=np.array([(aug[:, 4] == l).sum() for l in (0, 1, 2)]))
+                        label_counts=np.array([(aug[:, 4] == l).sum() for l in (0, 1, 2)]),
+                        label_counts_unfiltered=np.array([(o_int['full'][:, 4] == l).sum() for l in (0, 1, 2)]))
 
     # ---------------------------------------------------------------- wet ground (wet_ground/augmentation.py:25-161)
     pc = synthetic_cloud(seed=3, n_azimuth=256)
