@@ -129,6 +129,35 @@ LSS_API lss_status lss_snowfall_batch(lss_engine *e, int table_id, const float *
                               int32_t *d_out_counts, double *d_out_stats, float *d_out_full, int32_t *d_out_perm,
                               int32_t *d_out_nocc, void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_snowfall_workspace_bytes(int64_t n_total, int n_clouds);
+/* Host-to-host batched augment(): the reference's call shape (numpy cloud in -> numpy cloud out,
+ * simulation.py:427-544) for a batch.  h_points / h_out_* are HOST buffers (page-locked memory gives full PCIe speed;
+ * pageable works).  The batch is cut into `n_chunks` groups of whole clouds (<= 0: default 4) that flow through
+ * engine-owned streams and device buffers: H2D copy -> pre-pass -> beam stage -> D2H copy, the transfers and the
+ * pre-pass of one chunk overlapping the beam kernels of another.  Arguments and the slot-compacted output layout are
+ * those of lss_snowfall_batch (no d_theta / debug views); results are bit-identical to it for any n_chunks.
+ *
+ *   lss_snowfall_batch_host          synchronous; returns the batch's device status (LSS_ERR_RANGE_INDEX, ...) directly
+ *   lss_snowfall_batch_host_submit   enqueues the batch and returns a ticket; up to 3 batches may be in flight (the
+ *                                    4th submit without a wait fails with LSS_ERR_INVALID_ARG).  The host buffers must
+ *                                    stay valid and untouched until the ticket has been waited for.  With 2-3 batches
+ *                                    in flight -- a prefetching data loader -- batch k+1's copy-in, batch k's kernels
+ *                                    and batch k-1's copy-out run concurrently.
+ *   lss_snowfall_batch_host_wait     blocks until that batch's results are in its host buffers; returns its status   */
+LSS_API lss_status lss_snowfall_batch_host(lss_engine *e, int table_id, const float *h_points,
+                                           const int64_t *h_cloud_offsets, int n_clouds, const int32_t *h_order,
+                                           double beam_divergence_deg, const double *h_thresh_poly, double noise_floor,
+                                           uint32_t flags, int n_chunks, float *h_out_points, int32_t *h_out_counts,
+                                           double *h_out_stats);
+LSS_API lss_status lss_snowfall_batch_host_submit(lss_engine *e, int table_id, const float *h_points,
+                                                  const int64_t *h_cloud_offsets, int n_clouds, const int32_t *h_order,
+                                                  double beam_divergence_deg, const double *h_thresh_poly,
+                                                  double noise_floor, uint32_t flags, int n_chunks, float *h_out_points,
+                                                  int32_t *h_out_counts, double *h_out_stats, int *ticket_out);
+LSS_API lss_status lss_snowfall_batch_host_wait(lss_engine *e, int ticket);
+/* Diagnostic: device timeline of the most recently waited batch.  out[4*c + k] = milliseconds from the batch's first
+ * enqueued operation until chunk c's rows are on the device (k=0), its threshold polynomial is ready (1), its beam stage
+ * is done (2), its results are on the host (3).  Returns the number of chunks written (<= cap_chunks).               */
+LSS_API int lss_host_pipe_trace(lss_engine *e, float *out, int cap_chunks);
 /* Synchronises `stream`, then returns and clears the latched asynchronous device status.                          */
 LSS_API lss_status lss_check_async(lss_engine *e, void *stream);
 /* number of kernel launches the engine has enqueued since creation (bench.py's gpu_launches) */

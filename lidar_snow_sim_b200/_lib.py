@@ -59,6 +59,12 @@ SIGNATURES = [
     ('lss_snowfall_batch', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_double, _P, _P, _c.c_double,
                                       _c.c_uint32, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),
     ('lss_snowfall_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
+    ('lss_host_pipe_trace', _c.c_int, [_P, _P, _c.c_int]),
+    ('lss_snowfall_batch_host', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_double, _P, _c.c_double, _c.c_uint32,
+                                           _c.c_int, _P, _P, _P]),
+    ('lss_snowfall_batch_host_submit', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_double, _P, _c.c_double,
+                                                  _c.c_uint32, _c.c_int, _P, _P, _P, _c.POINTER(_c.c_int)]),
+    ('lss_snowfall_batch_host_wait', _c.c_int, [_P, _c.c_int]),
     ('lss_check_async', _c.c_int, [_P, _P]),
     ('lss_launch_count', _c.c_int64, [_P]),
     ('lss_debug_range_grid', _c.c_int, [_P]),

@@ -5,12 +5,6 @@
 
 namespace {
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
 // R = np.round(np.linspace(0, 120 + c*tau_h, 1230), 2)            (tools/snowfall/simulation.py:111-116)
 // np.linspace: y[k] = k * (stop/1229), y[-1] = stop; np.round(y, 2) = rint(y * 100) / 100.
 void host_range_grid(double *R)
@@ -86,6 +80,11 @@ void lss_destroy(lss_engine *e)
     cudaFree(e->d_status);
     cudaFree(e->d_sensor);
     cudaFree(e->d_camera);
+    lss_host_pipe_free(e);
+    for (auto &sl : e->stage) {
+        if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); }
+        if (sl.host) cudaFreeHost(sl.host);
+    }
     delete e;
 }
 
@@ -267,7 +266,7 @@ lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const 
     if (workspace_bytes < off_bytes + lss_prepass_ws_bytes(h_cloud_offsets[n_clouds], n_clouds))
         return lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small");
     int64_t *d_off = (int64_t *)d_workspace;
-    LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, h_cloud_offsets, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
+    LSS_CUDA_CHECK(e, lss_stage_upload(e, d_off, h_cloud_offsets, sizeof(int64_t) * (n_clouds + 1), st));
     return lss_prepass_run(e, d_points, d_off, nullptr, h_cloud_offsets, n_clouds, 0.5, noise_floor, 0, 0, 1, h_plane_in, d_poly_out,
                            d_plane_out, (char *)d_workspace + off_bytes, workspace_bytes - off_bytes, nullptr, st);
 }

@@ -680,13 +680,17 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
     for (int b = 0; b < B; b++) max_n = std::max<int64_t>(max_n, h_cloud_off[b + 1] - h_cloud_off[b]);
     int nblk = (int)std::min<int64_t>(L.max_blocks, std::max<int64_t>(1, (max_n + PP_TPB * 8 - 1) / (PP_TPB * 8)));
 
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(a.cp, 0, sizeof(CloudPre) * B, stream));
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(a.hist, 0, (size_t)B * HIST_NX * HIST_NY * 4, stream));
+    {
+        ZeroRegions z;
+        z.add(a.cp, sizeof(CloudPre) * B);
+        z.add(a.hist, (size_t)B * HIST_NX * HIST_NY * 4);
+        LSS_CUDA_CHECK(e, lss_zero_async(e, z, stream));
+    }
     {
         KernelTimer kt(e, LSS_K_PREPASS, stream);
         if (h_plane_in) {
             double *d_plane = (double *)(ws + L.plane_in);
-            LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_plane, h_plane_in, sizeof(double) * 4 * B, cudaMemcpyHostToDevice, stream));
+            LSS_CUDA_CHECK(e, lss_stage_upload(e, d_plane, h_plane_in, sizeof(double) * 4 * B, stream));
             k_set_plane<<<(B + 127) / 128, 128, 0, stream>>>(a, d_plane);
         } else {
             std::vector<int32_t> h_tb(B + 1, 0);
@@ -696,7 +700,7 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
                 h_tb[b + 1] = h_tb[b] + t;
                 max_tiles = std::max(max_tiles, t);
             }
-            LSS_CUDA_CHECK(e, cudaMemcpyAsync(ws + L.tile_base, h_tb.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, stream));
+            LSS_CUDA_CHECK(e, lss_stage_upload(e, ws + L.tile_base, h_tb.data(), sizeof(int32_t) * (B + 1), stream));
             k_window_tiles<<<dim3(max_tiles, B), WTILE, 0, stream>>>(a);
             k_window_gather<<<B, 1024, sizeof(int) * (max_tiles + 1), stream>>>(a);
             e->launches++;

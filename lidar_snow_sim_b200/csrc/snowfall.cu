@@ -780,7 +780,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
             return lss_fail(e, LSS_ERR_NO_TABLE, "order[] names a plane that is not in the table set");
     const WsLayout w = ws_layout(N, B);
     if (s.workspace_bytes < w.total || !s.d_workspace) return lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small");
-    if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && !s.h_thresh_poly && !(s.flags & LSS_FLAG_DEVICE_PREPASS))
+    if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && !s.h_thresh_poly && !s.d_thresh_poly && !(s.flags & LSS_FLAG_DEVICE_PREPASS))
         return lss_fail(e, LSS_ERR_INVALID_ARG, "threshold filter needs h_thresh_poly or LSS_FLAG_DEVICE_PREPASS");
     if ((s.flags & LSS_FLAG_CAMERA_FOV) && !e->has_camera)
         return lss_fail(e, LSS_ERR_NO_SENSOR, "camera calibration not set");
@@ -810,22 +810,29 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     unsigned *d_att_cnt = (unsigned *)(ws + w.counters + align_up((int64_t)B * 2 * 4, 8));
     unsigned long long *d_att_sum = (unsigned long long *)((char *)d_att_cnt + (int64_t)B * LSS_N_CHANNELS * 4);
 
-    LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, s.h_cloud_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, stream));
-    LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_tile_base, h_tile_base.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, stream));
-    LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_order, s.h_order, sizeof(int32_t) * B * LSS_N_CHANNELS, cudaMemcpyHostToDevice, stream));
-    if (s.h_thresh_poly)
-        LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_thresh, s.h_thresh_poly, sizeof(double) * 3 * B, cudaMemcpyHostToDevice, stream));
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_counters, 0, w.counters_bytes, stream));
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(s.d_out_stats, 0, sizeof(double) * 4 * B, stream));
-    if (N == 0 || B == 0) {
-        if (B) LSS_CUDA_CHECK(e, cudaMemsetAsync(s.d_out_counts, 0, sizeof(int32_t) * B, stream));
-        return LSS_OK;
+    LSS_CUDA_CHECK(e, lss_stage_upload(e, d_off, s.h_cloud_offsets, sizeof(int64_t) * (B + 1), stream));
+    LSS_CUDA_CHECK(e, lss_stage_upload(e, d_tile_base, h_tile_base.data(), sizeof(int32_t) * (B + 1), stream));
+    LSS_CUDA_CHECK(e, lss_stage_upload(e, d_order, s.h_order, sizeof(int32_t) * B * LSS_N_CHANNELS, stream));
+    if (s.h_thresh_poly && !s.d_thresh_poly)
+        LSS_CUDA_CHECK(e, lss_stage_upload(e, d_thresh, s.h_thresh_poly, sizeof(double) * 3 * B, stream));
+    int *d_counts2 = (int *)(ws + w.ovf);                                   // [0] solve list, [1] overflow list
+    {
+        ZeroRegions z;
+        z.add(d_counters, w.counters_bytes);
+        z.add(s.d_out_stats, sizeof(double) * 4 * B);
+        if (N == 0 || B == 0) {
+            z.add(s.d_out_counts, sizeof(int32_t) * B);
+            LSS_CUDA_CHECK(e, lss_zero_async(e, z, stream));
+            return LSS_OK;
+        }
+        const size_t hist_bytes = (size_t)h_tile_base[B] * NBINS * sizeof(unsigned);
+        z.add(d_hist_keep, hist_bytes);
+        z.add(d_hist_all, hist_bytes);
+        z.add(d_counts2, 2 * sizeof(int));
+        LSS_CUDA_CHECK(e, lss_zero_async(e, z, stream));
     }
-    const size_t hist_bytes = (size_t)h_tile_base[B] * NBINS * sizeof(unsigned);
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_hist_keep, 0, hist_bytes, stream));
-    if (d_hist_all) LSS_CUDA_CHECK(e, cudaMemsetAsync(d_hist_all, 0, hist_bytes, stream));
 
-    if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly) {
+    if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly && !s.d_thresh_poly) {
         // plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given
         lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
                                         nullptr, d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, stream);
@@ -844,7 +851,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.theta = s.d_theta;
     a.cloud_off = d_off;
     a.order = d_order;
-    a.thresh = d_thresh;
+    a.thresh = s.d_thresh_poly ? s.d_thresh_poly : d_thresh;
     a.sensor = e->d_sensor;
     a.camera = e->d_camera;
     a.R = e->d_R;
@@ -863,10 +870,8 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.att_cnt = d_att_cnt;
     a.att_sum = d_att_sum;
     a.status = e->d_status;
-    int *d_counts2 = (int *)(ws + w.ovf);                                   // [0] solve list, [1] overflow list
     unsigned long long *d_ovf_list = (unsigned long long *)(ws + w.ovf + 256);
     unsigned long long *d_solve_list = d_ovf_list + OVF_LIST_CAP;
-    LSS_CUDA_CHECK(e, cudaMemsetAsync(d_counts2, 0, 2 * sizeof(int), stream));
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
         // 1. scan: all beams; the ones without occluders are finished, the others go to the solve list

@@ -185,7 +185,9 @@ lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int6
     const int B = n_clouds;
     const int64_t N = h_cloud_offsets[B];
     if (B == 0 || N == 0) {
-        if (B) cudaMemsetAsync(d_out_counts, 0, sizeof(int32_t) * B, (cudaStream_t)stream);
+        ZeroRegions z;
+        z.add(d_out_counts, sizeof(int32_t) * B);
+        lss_zero_async(e, z, (cudaStream_t)stream);
         return LSS_OK;
     }
     if (!d_points) return lss_fail(e, LSS_ERR_INVALID_ARG, "null points");
@@ -199,7 +201,7 @@ lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int6
         if (workspace_bytes < L.total) { rc = lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small"); break; }
         char *ws = (char *)d_workspace;
         int64_t *d_off = (int64_t *)(ws + L.off);
-        if (cudaMemcpyAsync(d_off, h_cloud_offsets, sizeof(int64_t) * (B + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        if (lss_stage_upload(e, d_off, h_cloud_offsets, sizeof(int64_t) * (B + 1), st) != cudaSuccess) {
             rc = lss_fail(e, LSS_ERR_CUDA, "memcpy failed");
             break;
         }

@@ -211,66 +211,68 @@ class SnowfallEngine:
         _lib.check(st, self.h)
         return out
 
-    def snowfall_batch_host(self, table_id, host_points, cloud_offsets, order, beam_divergence_deg, host_out=None,
-                            n_chunks=4, n_slots=4, **kw):
+    def snowfall_batch_host_submit(self, table_id, host_points, cloud_offsets, order, beam_divergence_deg,
+                                   host_out=None, n_chunks=4, thresh_poly=None, noise_floor=0.7, threshold_filter=True,
+                                   camera_fov=False, device_prepass=False):
         """
-        Host-to-host batched augment(): `host_points` is a pinned CPU float32 (N, 5) tensor.  The batch is cut into
-        `n_chunks` groups of whole clouds that flow through `n_slots` independent streams (H2D copy, kernels, D2H copy
-        each in stream order), so that the PCIe transfers of one chunk overlap the kernels of another.
-        Returns dict(points, counts, stats) of pinned CPU tensors in the slot-compacted layout; synchronises.
+        Enqueue a host-to-host batched augment() (`lss_snowfall_batch_host_submit`) and return a ticket for
+        `snowfall_batch_host_wait`.  `host_points`: CPU float32 (N, 5) tensor or numpy array (pinned memory gives full
+        PCIe speed).  The batch is cut into `n_chunks` groups of whole clouds that flow through the engine's native
+        pipeline (H2D copy, pre-pass, beam stage, D2H copy on separate streams).  Up to 3 batches may be in flight; with
+        2-3 in flight (a prefetching loader) batch k+1's copy-in, batch k's kernels and batch k-1's copy-out overlap.
+        The input and `host_out` buffers must not be touched until the ticket has been waited for.
         """
         off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
         B = off.shape[0] - 1
         N = int(off[-1])
+        if isinstance(host_points, np.ndarray):
+            host_points = torch.from_numpy(np.ascontiguousarray(host_points, dtype=np.float32))
         assert not host_points.is_cuda and host_points.dtype == torch.float32 and host_points.shape == (N, 5)
+        assert host_points.is_contiguous()
         order = np.ascontiguousarray(order, dtype=np.int32).reshape(B, 64)
-        tp = kw.pop('thresh_poly', None)
-        if tp is not None:
-            tp = np.ascontiguousarray(tp, dtype=np.float64).reshape(B, 3)
+        tp = None
+        if thresh_poly is not None:
+            tp = np.ascontiguousarray(thresh_poly, dtype=np.float64).reshape(B, 3)
+        flags = 0
+        if threshold_filter:
+            flags |= _lib.FLAG_THRESHOLD_FILTER
+        if camera_fov:
+            flags |= _lib.FLAG_CAMERA_FOV
+        if device_prepass:
+            flags |= _lib.FLAG_DEVICE_PREPASS
         if host_out is None:
             host_out = {}
         if 'points' not in host_out:
             host_out['points'] = torch.empty((N, 5), dtype=torch.float32).pin_memory()
             host_out['counts'] = torch.empty((B,), dtype=torch.int32).pin_memory()
             host_out['stats'] = torch.empty((B, 4), dtype=torch.float64).pin_memory()
-        n_chunks = max(1, min(n_chunks, B))
-        bounds = [round(c * B / n_chunks) for c in range(n_chunks + 1)]
-        max_rows = max(int(off[bounds[c + 1]] - off[bounds[c]]) for c in range(n_chunks))
-        max_b = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
-        key = (max_rows, max_b, n_slots)
-        with torch.cuda.device(self.device):
-            if getattr(self, '_host_slots_key', None) != key:
-                need = self.lib.lss_snowfall_workspace_bytes(max_rows, max_b)
-                self._host_slots = [dict(stream=torch.cuda.Stream(self.device),
-                                         d_in=torch.empty((max_rows, 5), dtype=torch.float32, device=self.device),
-                                         ws=torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device),
-                                         out=dict(points=torch.empty((max_rows, 5), dtype=torch.float32, device=self.device),
-                                                  counts=torch.empty((max_b,), dtype=torch.int32, device=self.device),
-                                                  stats=torch.empty((max_b, 4), dtype=torch.float64, device=self.device)))
-                                    for _ in range(n_slots)]
-                self._host_slots_key = key
-            cur = torch.cuda.current_stream(self.device)
-            for sl in self._host_slots:
-                sl['stream'].wait_stream(cur)
-            for c in range(n_chunks):
-                sl = self._host_slots[c % n_slots]
-                b0, b1 = bounds[c], bounds[c + 1]
-                r0, r1 = int(off[b0]), int(off[b1])
-                nb, nr = b1 - b0, r1 - r0
-                with torch.cuda.stream(sl['stream']):
-                    d_in = sl['d_in'][:nr]
-                    d_in.copy_(host_points[r0:r1], non_blocking=True)
-                    out = dict(points=sl['out']['points'][:nr], counts=sl['out']['counts'][:nb],
-                               stats=sl['out']['stats'][:nb])
-                    self.snowfall_batch(table_id, d_in, off[b0:b1 + 1] - off[b0], order[b0:b1], beam_divergence_deg,
-                                        thresh_poly=None if tp is None else tp[b0:b1], out=out, workspace=sl['ws'], **kw)
-                    host_out['points'][r0:r1].copy_(out['points'], non_blocking=True)
-                    host_out['counts'][b0:b1].copy_(out['counts'], non_blocking=True)
-                    host_out['stats'][b0:b1].copy_(out['stats'], non_blocking=True)
-            for sl in self._host_slots:
-                cur.wait_stream(sl['stream'])
-        self.check()
-        return host_out
+        assert host_out['points'].shape == (N, 5) and host_out['counts'].shape == (B,)
+        ticket = ctypes.c_int(-1)
+        st = self.lib.lss_snowfall_batch_host_submit(
+            self.h, int(table_id), _ptr(host_points), _ptr(off), B, _ptr(order), float(beam_divergence_deg), _ptr(tp),
+            float(noise_floor), flags, int(n_chunks), _ptr(host_out['points']), _ptr(host_out['counts']),
+            _ptr(host_out['stats']), ctypes.byref(ticket))
+        _lib.check(st, self.h)
+        # the ticket keeps the buffers of the in-flight batch alive
+        return dict(id=int(ticket.value), out=host_out, keep=(host_points, off, order, tp))
+
+    def snowfall_batch_host_wait(self, ticket):
+        """Block until the batch is in its host buffers; raises what the reference would have raised for it.
+        Returns dict(points, counts, stats): pinned CPU tensors, slot-compacted layout of snowfall_batch."""
+        _lib.check(self.lib.lss_snowfall_batch_host_wait(self.h, int(ticket['id'])), self.h)
+        return ticket['out']
+
+    def snowfall_batch_host(self, table_id, host_points, cloud_offsets, order, beam_divergence_deg, **kw):
+        """Synchronous host-to-host batched augment(): submit + wait (see snowfall_batch_host_submit)."""
+        return self.snowfall_batch_host_wait(
+            self.snowfall_batch_host_submit(table_id, host_points, cloud_offsets, order, beam_divergence_deg, **kw))
+
+    def host_pipeline_trace(self, max_chunks=64):
+        """Device timeline (ms since call start) of the last snowfall_batch_host call: rows (n_chunks, 4) =
+        rows landed, polynomial ready, beam stage done, results on host."""
+        buf = np.zeros((max_chunks, 4), dtype=np.float32)
+        n = self.lib.lss_host_pipe_trace(self.h, _ptr(buf), max_chunks)
+        return buf[:n]
 
     def noise_threshold_poly(self, points, cloud_offsets, noise_floor=0.7, plane=None):
         """Device pre-pass only: returns (poly (B,3) float64 tensor in np.polyfit order, plane (B,4) tensor).

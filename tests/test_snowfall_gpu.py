@@ -299,7 +299,31 @@ def test_full_size_properties(engine, tables18k):
 
 
 def test_host_pipeline_matches_device(engine, tables18k):
-    """snowfall_batch_host (pinned host in/out, chunked over streams) == snowfall_batch on device-resident input."""
+    """lss_snowfall_batch_host (host in/out, chunks over the engine's copy / pre-pass / beam streams) == snowfall_batch
+    on device-resident input, bit for bit, for any chunking; ragged batch with an empty cloud in it."""
+    B = 7
+    clouds = [synthetic_cloud(seed=300 + b, n_azimuth=256 + 64 * b) for b in range(B)]
+    clouds[3] = clouds[3][:0]
+    off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+    orders = np.stack([np.random.default_rng(b).permutation(64) for b in range(B)]).astype(np.int32)
+    host = torch.from_numpy(np.concatenate(clouds)).pin_memory()
+    tid = engine.upload_tables(tables18k)
+    poly = np.tile(np.array([1e-4, -2e-3, 0.02]), (B, 1))
+    for kw in (dict(thresh_poly=poly), dict(threshold_filter=False)):
+        dev = engine.snowfall_batch(tid, host.cuda(), off, orders, DIV, **kw)
+        engine.check()
+        dev = {k: v.cpu() for k, v in dev.items()}
+        for chunks, src in ((1, host), (3, host.numpy().copy()), (7, host), (0, host), (50, host)):
+            got = engine.snowfall_batch_host(tid, src, off, orders, DIV, n_chunks=chunks, **kw)
+            assert torch.equal(got['counts'], dev['counts']) and torch.equal(got['stats'], dev['stats'])
+            for b in range(B):
+                n = int(dev['counts'][b])
+                assert torch.equal(got['points'][off[b]:off[b] + n], dev['points'][off[b]:off[b] + n])
+    engine.free_tables(tid)
+
+
+def test_host_pipeline_device_prepass(engine, tables18k):
+    """Same with the device pre-pass running on the pipeline's own streams (needs ground: no empty cloud)."""
     B = 6
     clouds = [synthetic_cloud(seed=300 + b, n_azimuth=256 + 64 * b) for b in range(B)]
     off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
@@ -309,12 +333,65 @@ def test_host_pipeline_matches_device(engine, tables18k):
     dev = engine.snowfall_batch(tid, host.cuda(), off, orders, DIV, device_prepass=True)
     engine.check()
     dev = {k: v.cpu() for k, v in dev.items()}
-    for chunks in (1, 4, 6):
-        got = engine.snowfall_batch_host(tid, host, off, orders, DIV, device_prepass=True, n_chunks=chunks)
+    out = {}
+    for chunks in (1, 4, 6, 4):
+        got = engine.snowfall_batch_host(tid, host, off, orders, DIV, device_prepass=True, n_chunks=chunks, host_out=out)
         assert torch.equal(got['counts'], dev['counts']) and torch.equal(got['stats'], dev['stats'])
         for b in range(B):
             n = int(dev['counts'][b])
             assert torch.equal(got['points'][off[b]:off[b] + n], dev['points'][off[b]:off[b] + n])
+    # a device-side error inside one chunk surfaces as the reference's exception type from the synchronous call
+    far = clouds[0].copy()
+    far[:, :3] *= (125.0 / np.linalg.norm(far[:, :3], axis=1))[:, None]     # returns beyond the 1230-sample grid
+    with pytest.raises(IndexError):
+        engine.snowfall_batch_host(tid, np.concatenate([clouds[1], far]), np.array([0, len(clouds[1]), len(clouds[1]) + len(far)]),
+                                   orders[:2], DIV, threshold_filter=False, n_chunks=2)
+    got = engine.snowfall_batch_host(tid, host, off, orders, DIV, device_prepass=True, n_chunks=3)   # engine still usable
+    assert torch.equal(got['counts'], dev['counts'])
+    engine.free_tables(tid)
+
+
+def test_host_pipeline_batches_in_flight(engine, tables18k):
+    """submit / wait: three batches in flight at once (one of them failing on the device) give the same results as the
+    synchronous call; the error belongs to the batch that caused it; a fourth submit or a second wait is refused."""
+    tid = engine.upload_tables(tables18k)
+    batches = []
+    for k in range(3):
+        clouds = [synthetic_cloud(seed=700 + 10 * k + b, n_azimuth=192 + 64 * k) for b in range(3 + k)]
+        if k == 1:
+            far = clouds[1]
+            far[:, :3] *= (125.0 / np.linalg.norm(far[:, :3], axis=1))[:, None]         # IndexError batch
+        off = np.concatenate([[0], np.cumsum([c.shape[0] for c in clouds])]).astype(np.int64)
+        orders = np.stack([np.random.default_rng(50 + b).permutation(64) for b in range(len(clouds))]).astype(np.int32)
+        batches.append((torch.from_numpy(np.concatenate(clouds)).pin_memory(), off, orders))
+    poly = np.array([1e-4, -2e-3, 0.02])
+    want = []
+    for k, (host, off, orders) in enumerate(batches):
+        if k == 1:
+            want.append(None)
+            continue
+        r = engine.snowfall_batch(tid, host.cuda(), off, orders, DIV, thresh_poly=np.tile(poly, (len(off) - 1, 1)))
+        engine.check()
+        want.append({n: v.cpu() for n, v in r.items()})
+    for rep in range(2):                                        # second round reuses the slots
+        tickets = [engine.snowfall_batch_host_submit(tid, host, off, orders, DIV, n_chunks=2,
+                                                     thresh_poly=np.tile(poly, (len(off) - 1, 1)))
+                   for host, off, orders in batches]
+        with pytest.raises(ValueError):                         # a fourth batch needs a wait first
+            engine.snowfall_batch_host_submit(tid, *batches[0], DIV, n_chunks=1, threshold_filter=False)
+        for k in (0, 2, 1):                                     # any order
+            if k == 1:
+                with pytest.raises(IndexError):
+                    engine.snowfall_batch_host_wait(tickets[k])
+                continue
+            got = engine.snowfall_batch_host_wait(tickets[k])
+            off = batches[k][1]
+            assert torch.equal(got['counts'], want[k]['counts']) and torch.equal(got['stats'], want[k]['stats'])
+            for b in range(len(off) - 1):
+                n = int(got['counts'][b])
+                assert torch.equal(got['points'][off[b]:off[b] + n], want[k]['points'][off[b]:off[b] + n])
+        with pytest.raises(ValueError):
+            engine.snowfall_batch_host_wait(tickets[0])
     engine.free_tables(tid)
 
 
