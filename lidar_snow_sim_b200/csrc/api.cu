@@ -81,6 +81,8 @@ void lss_destroy(lss_engine *e)
     cudaFree(e->d_sensor);
     cudaFree(e->d_camera);
     lss_host_pipe_free(e);
+    for (cudaStream_t st : e->side) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t ev : e->side_ev) if (ev) cudaEventDestroy(ev);
     for (auto &sl : e->stage) {
         if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); }
         if (sl.host) cudaFreeHost(sl.host);
@@ -297,7 +299,7 @@ lss_status lss_set_profiling(lss_engine *e, int enable)
     return LSS_OK;
 }
 
-static const char *kernel_names[LSS_K_COUNT] = {"channel_sort", "prepass", "snowfall", "compact", "finalize", "wet_ground"};
+static const char *kernel_names[LSS_K_COUNT] = {"channel_sort", "prepass", "snowfall", "compact", "keep", "wet_ground"};
 
 const char *lss_kernel_name(int kernel) { return (kernel >= 0 && kernel < LSS_K_COUNT) ? kernel_names[kernel] : ""; }
 

@@ -84,9 +84,32 @@ struct lss_engine {
     static constexpr int N_STAGE = 256;
     StageSlot stage[N_STAGE];
     int stage_next = 0;
+    // high-priority side streams for work forked off the caller's stream (the pre-pass next to the beam kernels)
+    static constexpr int N_SIDE = 4;
+    cudaStream_t side[N_SIDE] = {};
+    cudaEvent_t side_ev[2 * 32] = {};
+    int side_next = 0;
     struct lss_host_pipe *pipe = nullptr;   // streams + device buffers of lss_snowfall_batch_host (host_pipeline.cu)
 };
 void lss_host_pipe_free(lss_engine *e);
+
+// next side stream + a (fork, join) event pair, round robin; created on first use
+inline cudaError_t lss_side_stream(lss_engine *e, cudaStream_t *stream, cudaEvent_t *ev_fork, cudaEvent_t *ev_join)
+{
+    cudaError_t err;
+    const int k = e->side_next++;
+    cudaStream_t &s = e->side[k % lss_engine::N_SIDE];
+    if (!s) {
+        int least = 0, greatest = 0;
+        if ((err = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return err;
+        if ((err = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest)) != cudaSuccess) return err;
+    }
+    cudaEvent_t *ev = &e->side_ev[2 * (k % 32)];
+    for (int j = 0; j < 2; j++)
+        if (!ev[j] && (err = cudaEventCreateWithFlags(&ev[j], cudaEventDisableTiming)) != cudaSuccess) return err;
+    *stream = s; *ev_fork = ev[0]; *ev_join = ev[1];
+    return cudaSuccess;
+}
 
 // Asynchronous host -> device upload of a small host array through the engine's pinned ring (stream ordered; the
 // caller's buffer may be reused as soon as this returns).  The transfer is a tiny kernel reading the mapped pinned slot,

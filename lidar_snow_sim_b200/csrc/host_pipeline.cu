@@ -8,8 +8,9 @@
 // A batch is cut into chunks of whole clouds.  Per chunk, in stream order:
 //
 //   copy-in stream    H2D of the chunk's rows                                    (PCIe, ~50 GB/s)
-//   pre-pass streams  ground plane + noise-threshold polynomial (prepass.cu)     latency bound, tiny grids, high priority
-//   beam streams      scan / solve / overflow / tile scan / scatter (snowfall.cu), chunks in order, lower priority
+//   beam streams      scan / solve / overflow / keep / tile scan / scatter (snowfall.cu), chunks in order, lower
+//                     priority; the pre-pass (prepass.cu) is forked by lss_snowfall_run onto the engine's high-priority
+//                     side streams and runs next to the beam kernels
 //   copy-out stream   D2H of the chunk's augmented rows, counts, stats
 //
 // so that within one batch the PCIe transfers overlap the kernels, and -- with two or three batches in flight, the
@@ -39,9 +40,9 @@ struct PipeSlot {
 };
 
 struct lss_host_pipe {
-    static constexpr int N_PRE = 4, N_BEAM = 4, N_SLOT = 3;
+    static constexpr int N_BEAM = 4, N_SLOT = 3;
     int n_beam = 2;                         // beam streams in use (env LSS_PIPE_BEAM_STREAMS)
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_pre[N_PRE] = {}, s_beam[N_BEAM] = {};
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_beam[N_BEAM] = {};
     PipeSlot slot[N_SLOT];
     int next_slot = 0;
     int last_slot = -1;                     // slot of the most recently completed batch (lss_host_pipe_trace)
@@ -50,7 +51,6 @@ struct lss_host_pipe {
 static void pipe_quiesce(lss_host_pipe *p)
 {
     if (p->s_h2d) cudaStreamSynchronize(p->s_h2d);
-    for (cudaStream_t s : p->s_pre) if (s) cudaStreamSynchronize(s);
     for (cudaStream_t s : p->s_beam) if (s) cudaStreamSynchronize(s);
     if (p->s_d2h) cudaStreamSynchronize(p->s_d2h);
 }
@@ -61,7 +61,6 @@ void lss_host_pipe_free(lss_engine *e)
     if (!p) return;
     pipe_quiesce(p);
     for (cudaStream_t s : {p->s_h2d, p->s_d2h}) if (s) cudaStreamDestroy(s);
-    for (cudaStream_t s : p->s_pre) if (s) cudaStreamDestroy(s);
     for (cudaStream_t s : p->s_beam) if (s) cudaStreamDestroy(s);
     for (PipeSlot &sl : p->slot) {
         for (cudaEvent_t v : sl.ev) cudaEventDestroy(v);
@@ -85,8 +84,6 @@ static cudaError_t pipe_create(lss_engine *e)
     if ((err = cudaDeviceGetStreamPriorityRange(&least, &greatest)) != cudaSuccess) return err;
     if ((err = cudaStreamCreateWithPriority(&p->s_h2d, cudaStreamNonBlocking, greatest)) != cudaSuccess) return err;
     if ((err = cudaStreamCreateWithPriority(&p->s_d2h, cudaStreamNonBlocking, greatest)) != cudaSuccess) return err;
-    for (auto &s : p->s_pre)
-        if ((err = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest)) != cudaSuccess) return err;
     const char *nb = getenv("LSS_PIPE_BEAM_STREAMS");
     p->n_beam = std::max(1, std::min((int)lss_host_pipe::N_BEAM, nb ? atoi(nb) : 2));
     for (int k = 0; k < lss_host_pipe::N_BEAM; k++)          // earlier chunks outrank later ones
@@ -168,11 +165,8 @@ extern "C" lss_status lss_snowfall_batch_host_submit(lss_engine *e, int table_id
         max_rows = std::max(max_rows, h_cloud_offsets[bounds[c + 1]] - h_cloud_offsets[bounds[c]]);
         max_b = std::max(max_b, bounds[c + 1] - bounds[c]);
     }
-    const bool device_prepass = (flags & LSS_FLAG_THRESHOLD_FILTER) && (flags & LSS_FLAG_DEVICE_PREPASS) && !h_thresh_poly;
     const int64_t snow_ws = (lss_snowfall_ws_bytes(max_rows, max_b) + 255) / 256 * 256;
-    const int64_t off_ws = ((int64_t)(max_b + 1) * 8 + 255) / 256 * 256;
-    const int64_t pre_ws = device_prepass ? off_ws + (lss_prepass_ws_bytes(max_rows, max_b) + 255) / 256 * 256 : 0;
-    const int64_t chunk_ws = snow_ws + pre_ws;
+    const int64_t chunk_ws = snow_ws;
     if (pipe_create(e) != cudaSuccess) {
         cudaGetLastError();
         return lss_fail(e, LSS_ERR_CUDA, "host pipeline: stream creation failed");
@@ -233,20 +227,7 @@ extern "C" lss_status lss_snowfall_batch_host_submit(lss_engine *e, int table_id
         a.d_workspace = ws;
         a.workspace_bytes = snow_ws;
 
-        if (device_prepass && nr > 0) {
-            cudaStream_t sp = p->s_pre[c % lss_host_pipe::N_PRE];
-            int64_t *d_off = (int64_t *)(ws + snow_ws);
-            ce = cudaStreamWaitEvent(sp, ev_in, 0);
-            if (ce == cudaSuccess) ce = lss_stage_upload(e, d_off, loc_off.data(), sizeof(int64_t) * (nb + 1), sp);
-            if (ce != cudaSuccess) { rc = lss_fail(e, LSS_ERR_CUDA, cudaGetErrorString(ce)); break; }
-            a.d_thresh_poly = sl.d_poly + 3 * (size_t)b0;
-            rc = lss_prepass_run(e, a.d_points, d_off, nullptr, loc_off.data(), nb, 0.5, noise_floor, 0, 0, 1, nullptr,
-                                 sl.d_poly + 3 * (size_t)b0, nullptr, ws + snow_ws + off_ws, pre_ws - off_ws, nullptr, sp);
-            if (rc != LSS_OK) break;
-            ce = cudaEventRecord(ev_pre, sp);
-        } else {
-            ce = cudaEventRecord(ev_pre, p->s_h2d);
-        }
+        ce = cudaEventRecord(ev_pre, p->s_h2d);      // (the pre-pass is forked next to the beam kernels by lss_snowfall_run)
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sb, ev_pre, 0);
         if (ce != cudaSuccess) { rc = lss_fail(e, LSS_ERR_CUDA, cudaGetErrorString(ce)); break; }
         rc = lss_snowfall_run(e, a, sb);

@@ -1,12 +1,18 @@
 // snowfall.cu -- batched snowfall augmentation on device-resident clouds.
 //
-// Pipeline per call (all on one stream):
-//   [pre-pass]       ground plane + noise-threshold polynomial (prepass.cu)     (tools/snowfall/simulation.py:449-467)
-//   k_snowfall       one thread per beam, beams in INPUT order: range/azimuth, candidate scan of ONE azimuth bucket of
-//                    the channel's snowflake plane, exact float64 disk/wedge test, nearest-first claiming of the beam's
+// Pipeline per call (on the caller's stream; the pre-pass is forked onto an engine side stream and joined before k_keep):
+//   [pre-pass]       ground plane + noise-threshold polynomial (prepass.cu), concurrent with the beam kernels
+//                                                                                 (tools/snowfall/simulation.py:449-467)
+//   k_snowfall<SCAN> one thread per beam, beams in INPUT order: range/azimuth, candidate scan of ONE azimuth bucket of
+//                    the channel's snowflake plane up to the first occluder; un-occluded beams are finished, the others
+//                    pushed to the solve list with a work class (target range)
+//   k_list_sort      counting sort of the solve list by work class (a solve warp runs as long as its slowest lane)
+//   k_snowfall<LIST> the listed beams: all occluders, exact float64 disk/wedge test, nearest-first claiming of the beam's
 //                    angular sub-intervals; then, warp-cooperatively, the summed sin^2 waveform + argmax; relabel / move
-//                    the point, threshold + FOV keep flag, statistics, per-tile channel histogram of the kept rows
-//                                                                                 (simulation.py:50-194, 231-424, 516-540)
+//                    the point; label-1 statistics                               (simulation.py:50-194, 231-424)
+//   k_snowfall<128>  beams with more than 24 occluders (rare)
+//   k_keep           threshold (original range) + FOV keep flag, per-tile channel histogram of the kept rows,
+//                    num_attenuated / num_removed                                 (simulation.py:516-540)
 //   k_tile_scan      per cloud: exclusive scan of the tile histograms -> destination of every (tile, channel) run;
 //                    kept-row count and stats (num_attenuated, num_removed, avg_intensity_diff)  (simulation.py:525-542)
 //   k_scatter        stable scatter of the kept rows to "sorted by channel, compacted" order -- the reference's
@@ -34,6 +40,8 @@ constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel
 // kernel modes
 constexpr int MODE_SCAN = 0;      // every beam of the batch: candidate scan; beams without occluders are finished here,
                                   // the others are pushed to the solve list
+constexpr int LIST_HDR_BYTES = 2048;  // ints: [0] solve count, [1] overflow count, [C..2C) class counts, [2C..3C) cursors
+constexpr int LIST_CLASSES = 128;  // solve list is counting-sorted by work class (target range) before the solve kernel
 constexpr int MODE_LIST = 1;      // one listed beam per thread (dense: every lane has occluders): scan again, claim,
                                   // waveform, finish
 
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
         if (blockIdx.x * SNOW_TPB >= cnt) return;
         active = slot < cnt;
         const unsigned long long it = active ? a.list_in[slot] : 0ull;
-        b = (int)(it >> 32);
+        b = (int)((it >> 32) & 0xffffu);
         i = (int)(it & 0xffffffffu);
     } else {
         b = blockIdx.y;
@@ -285,7 +293,13 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
                 const int leader = __ffs(pm) - 1;
                 if (lane == leader) base = atomicAdd(a.count_out, __popc(pm));
                 base = __shfl_sync(pm, base, leader);
-                a.list_out[base + __popc(pm & ((1u << lane) - 1u))] = ((unsigned long long)b << 32) | (unsigned)i;
+                // work class of the beam: everything it costs the solve kernel (bucket prefix, occluders, samples)
+                // grows with the target range
+                const int cls = min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
+                a.list_out[base + __popc(pm & ((1u << lane) - 1u))] =
+                    ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
+                const unsigned cm = __match_any_sync(pm, cls);
+                if (lane == __ffs(cm) - 1) atomicAdd(a.count_out + LIST_CLASSES + cls, __popc(cm));
                 deferred = true;
             }
         }
@@ -522,39 +536,11 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
         out_i = (float)ci;
     }
 
-    // ---- cloud-level post: round, threshold, FOV (simulation.py:516-540) ------------------------------------------
-    bool keep = active;
-    bool keep_thr = active;      // kept by the threshold filter: num_attenuated is counted BEFORE the FOV filter (:525)
-    bool removed = false;
+    // ---- np.round of the intensity column (simulation.py:516); the threshold / FOV filters, which need the pre-pass
+    // polynomial, are applied by k_keep so that the pre-pass can run next to the beam kernels -------------------------
     if (active) {
         out_i = rintf(out_i);
-        if (a.flags & LSS_FLAG_THRESHOLD_FILTER) {
-            const double *p = a.thresh + 3 * b;
-            const double d2 = (double)__fmul_rn(d32, d32);
-            const double thr = __dadd_rn(__dadd_rn(__dmul_rn(p[0], d2), __dmul_rn(p[1], d)), p[2]);
-            keep = (out_l == 2.0f) || ((double)out_i > thr);
-        }
-        keep_thr = keep;
-        if (keep && (a.flags & LSS_FLAG_CAMERA_FOV)) {
-            const float *M = a.camera->M, *P2 = a.camera->P2;
-            float rx = fmaf(out_z, M[6], fmaf(out_y, M[3], out_x * M[0])) + M[9];
-            float ry = fmaf(out_z, M[7], fmaf(out_y, M[4], out_x * M[1])) + M[10];
-            float rz = fmaf(out_z, M[8], fmaf(out_y, M[5], out_x * M[2])) + M[11];
-            float u = fmaf(rz, P2[2], fmaf(ry, P2[1], rx * P2[0])) + P2[3];
-            float v = fmaf(rz, P2[6], fmaf(ry, P2[5], rx * P2[4])) + P2[7];
-            float wd = fmaf(rz, P2[10], fmaf(ry, P2[9], rx * P2[8])) + P2[11];
-            u = u / rz;
-            v = v / rz;
-            const float depth = wd - P2[11];
-            keep = (u >= 0.0f) && (u < (float)a.camera->img_w) && (v >= 0.0f) && (v < (float)a.camera->img_h) &&
-                   (depth >= 0.0f);
-        }
-        removed = !keep;
-        if (!deferred) {
-            a.code_keep[beg + i] = keep ? (uint8_t)ch : (uint8_t)255;
-            if (a.code_all) a.code_all[beg + i] = (uint8_t)ch;
-            if (a.nocc) a.nocc[beg + i] = n_claim;
-        }
+        if (!deferred && a.nocc) a.nocc[beg + i] = n_claim;
     }
     const bool counted = active && !deferred;      // a deferred beam is accounted for by the overflow kernel
     if (SLOW) {
@@ -563,18 +549,11 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
             float *row = a.aug + (beg + i) * 5;
             row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
         }
-        auto agg_add = [&](bool on, int key, unsigned *base_ptr) {          // base_ptr[key] += #lanes with this key
-            const unsigned m = __match_any_sync(0xffffffffu, on ? key : -1);
-            if (on && lane == __ffs(m) - 1) atomicAdd(base_ptr + key, (unsigned)__popc(m));
-        };
-        const int hrow = counted ? (a.tile_base[b] + i / TILE) * NBINS + ch : 0;
-        agg_add(counted && keep, hrow, a.hist_keep);
-        if (a.hist_all) agg_add(counted, hrow, a.hist_all);
-        agg_add(counted && att_new_i >= 0, b * LSS_N_CHANNELS + (ch < LSS_N_CHANNELS ? ch : 0), a.att_cnt);
-        agg_add(counted && keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS, 2 * b, (unsigned *)a.counters);
-        agg_add(counted && removed, 2 * b + 1, (unsigned *)a.counters);
         {
             const bool on = counted && att_new_i >= 0;
+            const int key = b * LSS_N_CHANNELS + (ch < LSS_N_CHANNELS ? ch : 0);
+            const unsigned mk = __match_any_sync(0xffffffffu, on ? key : -1);
+            if (on && lane == __ffs(mk) - 1) atomicAdd(a.att_cnt + key, (unsigned)__popc(mk));
             const unsigned m = __match_any_sync(0xffffffffu, on ? b : -1);
             const unsigned sum = __reduce_add_sync(m, on ? (unsigned)att_new_i : 0u);
             if (on && lane == __ffs(m) - 1) atomicAdd(&a.att_sum[b], (unsigned long long)sum);
@@ -593,26 +572,11 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
 #pragma unroll
         for (int q = 0; q < 5; q++) {
             const int f = q * 32 + lane;
-            if (f < nf_w) dst[f] = s_rows[wid][f];              // read back by k_scatter from L2
+            if (f < nf_w) dst[f] = s_rows[wid][f];              // read back by k_keep / k_scatter from L2
         }
     }
-    // per-tile channel histograms for the scatter pass (warp-aggregated)
-    {
-        const int tile = blk0 / TILE;
-        unsigned *hk = a.hist_keep + ((size_t)a.tile_base[b] + tile) * NBINS;
-        const int ck = (counted && keep) ? ch : -1;
-        const unsigned mk = __match_any_sync(0xffffffffu, ck);
-        if (ck >= 0 && lane == __ffs(mk) - 1) atomicAdd(&hk[ck], (unsigned)__popc(mk));
-        if (a.hist_all) {
-            unsigned *ha = a.hist_all + ((size_t)a.tile_base[b] + tile) * NBINS;
-            const int ca = counted ? ch : -1;
-            const unsigned ma = __match_any_sync(0xffffffffu, ca);
-            if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&ha[ca], (unsigned)__popc(ma));
-        }
-    }
-    // per-cloud statistics: warp-aggregated integer atomics (order independent => bit-reproducible)
-    const unsigned m_att = __ballot_sync(0xffffffffu, counted && keep_thr && out_l == 1.0f && ch < LSS_N_CHANNELS);
-    const unsigned m_rem = __ballot_sync(0xffffffffu, counted && removed);
+    // label-1 beams per channel and the sum of their new intensities (simulation.py:170): integer atomics, order
+    // independent => bit-reproducible
     {
         const int ca = (counted && att_new_i >= 0) ? ch : -1;
         const unsigned ma = __match_any_sync(0xffffffffu, ca);
@@ -622,10 +586,124 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
         for (int s = 16; s > 0; s >>= 1) sn += __shfl_xor_sync(0xffffffffu, sn, s);
         if (lane == 0 && sn) atomicAdd(&a.att_sum[b], sn);
     }
-    if (lane == 0) {
-        if (m_att) atomicAdd(&a.counters[2 * b], __popc(m_att));
-        if (m_rem) atomicAdd(&a.counters[2 * b + 1], __popc(m_rem));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// counting sort of the solve list by work class, so that the 32 beams of a solve-kernel warp cost about the same
+// (the warp runs as long as its slowest lane).  hdr: [0] entries, [LIST_CLASSES + c] class counts (from the scan kernel),
+// [2 * LIST_CLASSES + c] class cursors.  Order inside a class is arbitrary: the results do not depend on list order.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_list_sort(const unsigned long long *__restrict__ in, unsigned long long *out,
+                                                    int *hdr, int cap)
+{
+    __shared__ int base[LIST_CLASSES];
+    const int cnt = min(hdr[0], cap);
+    if (blockIdx.x * 256 >= cnt) return;
+    if (threadIdx.x < 32) {                                  // exclusive scan of the class counts, one warp
+        int run = 0;
+        for (int c0 = 0; c0 < LIST_CLASSES; c0 += 32) {
+            const int v = hdr[LIST_CLASSES + c0 + threadIdx.x];
+            int incl = v;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, s);
+                if ((int)threadIdx.x >= s) incl += t;
+            }
+            base[c0 + threadIdx.x] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
+    __syncthreads();
+    const int slot = blockIdx.x * 256 + threadIdx.x;
+    const bool on = slot < cnt;
+    const unsigned long long it = on ? in[slot] : 0ull;
+    const int cls = on ? (int)(it >> 48) : -1;
+    const unsigned m = __match_any_sync(0xffffffffu, cls);
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int pos = 0;
+    if (on && lane == leader) pos = atomicAdd(&hdr[2 * LIST_CLASSES + cls], __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, leader);
+    if (on) out[base[cls] + pos + __popc(m & ((1u << lane) - 1u))] = it;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// keep pass: threshold filter on the ORIGINAL range (simulation.py:518-523), camera FOV filter (:532-537), per-tile
+// channel histograms for the scatter pass, num_attenuated / num_removed.  One CTA per tile of 1024 rows: the tile's
+// histogram rows are written, not accumulated, so they need no zero fill.  Runs after the beam kernels AND the
+// pre-pass (which may have run concurrently with them on another stream).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE) k_keep(DevArgs a)
+{
+    __shared__ unsigned h_keep[NBINS], h_all[NBINS];
+    __shared__ int s_cnt[2];
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int64_t beg = a.cloud_off[b];
+    const int n = (int)(a.cloud_off[b + 1] - beg);
+    if (tile * TILE >= n) return;
+    if (threadIdx.x < NBINS) { h_keep[threadIdx.x] = 0; h_all[threadIdx.x] = 0; }
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = tile * TILE + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = i < n;
+    bool keep = false, att = false;
+    int ch = -1;
+    if (active) {
+        const float *in = a.pts + (beg + i) * 5;
+        const float *row = a.aug + (beg + i) * 5;
+        const float px = __ldcs(in), py = __ldcs(in + 1), pz = __ldcs(in + 2);
+        ch = channel_bin(__ldcs(in + 4));
+        const float out_x = row[0], out_y = row[1], out_z = row[2], out_i = row[3], out_l = row[4];
+        keep = true;
+        if (a.flags & LSS_FLAG_THRESHOLD_FILTER) {
+            const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+            const double d = (double)d32;
+            const double *p = a.thresh + 3 * b;
+            const double d2 = (double)__fmul_rn(d32, d32);
+            const double thr = __dadd_rn(__dadd_rn(__dmul_rn(p[0], d2), __dmul_rn(p[1], d)), p[2]);
+            keep = (out_l == 2.0f) || ((double)out_i > thr);
+        }
+        att = keep && out_l == 1.0f && ch < LSS_N_CHANNELS;   // num_attenuated is counted BEFORE the FOV filter (:525)
+        if (keep && (a.flags & LSS_FLAG_CAMERA_FOV)) {
+            const float *M = a.camera->M, *P2 = a.camera->P2;
+            float rx = fmaf(out_z, M[6], fmaf(out_y, M[3], out_x * M[0])) + M[9];
+            float ry = fmaf(out_z, M[7], fmaf(out_y, M[4], out_x * M[1])) + M[10];
+            float rz = fmaf(out_z, M[8], fmaf(out_y, M[5], out_x * M[2])) + M[11];
+            float u = fmaf(rz, P2[2], fmaf(ry, P2[1], rx * P2[0])) + P2[3];
+            float v = fmaf(rz, P2[6], fmaf(ry, P2[5], rx * P2[4])) + P2[7];
+            float wd = fmaf(rz, P2[10], fmaf(ry, P2[9], rx * P2[8])) + P2[11];
+            u = u / rz;
+            v = v / rz;
+            const float depth = wd - P2[11];
+            keep = (u >= 0.0f) && (u < (float)a.camera->img_w) && (v >= 0.0f) && (v < (float)a.camera->img_h) &&
+                   (depth >= 0.0f);
+        }
+        a.code_keep[beg + i] = keep ? (uint8_t)ch : (uint8_t)255;
+        if (a.code_all) a.code_all[beg + i] = (uint8_t)ch;
+    }
+    // warp-aggregated shared-memory histograms
+    {
+        const int ck = (active && keep) ? ch : -1;
+        const unsigned mk = __match_any_sync(0xffffffffu, ck);
+        if (ck >= 0 && lane == __ffs(mk) - 1) atomicAdd(&h_keep[ck], (unsigned)__popc(mk));
+        if (a.hist_all) {
+            const unsigned ma = __match_any_sync(0xffffffffu, active ? ch : -1);
+            if (active && lane == __ffs(ma) - 1) atomicAdd(&h_all[ch], (unsigned)__popc(ma));
+        }
+        const unsigned m_att = __ballot_sync(0xffffffffu, att);
+        const unsigned m_rem = __ballot_sync(0xffffffffu, active && !keep);
+        if (lane == 0) {
+            if (m_att) atomicAdd(&s_cnt[0], __popc(m_att));
+            if (m_rem) atomicAdd(&s_cnt[1], __popc(m_rem));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NBINS) {
+        const size_t hrow = ((size_t)a.tile_base[b] + tile) * NBINS + threadIdx.x;
+        a.hist_keep[hrow] = h_keep[threadIdx.x];
+        if (a.hist_all) a.hist_all[hrow] = h_all[threadIdx.x];
+    }
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) atomicAdd(&a.counters[2 * b + threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -748,7 +826,7 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     w.counters_bytes = align_up((int64_t)n_clouds * 2 * 4, 8) + (int64_t)n_clouds * LSS_N_CHANNELS * 4 + (int64_t)n_clouds * 8;
     w.counters = o;   o = align_up(o + w.counters_bytes, 256);
     // counts (padded) | overflow list | solve list (every beam may have occluders)
-    w.ovf = o;        o = align_up(o + 256 + (int64_t)OVF_LIST_CAP * 8 + n_total * 8, 256);
+    w.ovf = o;        o = align_up(o + LIST_HDR_BYTES + (int64_t)OVF_LIST_CAP * 8 + 2 * n_total * 8, 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -825,18 +903,27 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
             LSS_CUDA_CHECK(e, lss_zero_async(e, z, stream));
             return LSS_OK;
         }
-        const size_t hist_bytes = (size_t)h_tile_base[B] * NBINS * sizeof(unsigned);
-        z.add(d_hist_keep, hist_bytes);
-        z.add(d_hist_all, hist_bytes);
-        z.add(d_counts2, 2 * sizeof(int));
+        z.add(d_counts2, LIST_HDR_BYTES);                 // (the tile histograms are written whole by k_keep)
         LSS_CUDA_CHECK(e, lss_zero_async(e, z, stream));
     }
 
+    // Device pre-pass: plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given.
+    // Only k_keep needs its result, so it is forked onto one of the engine's high-priority side streams and runs next
+    // to the beam kernels (a chain of small latency-bound kernels that fits into the SMs as beam CTAs retire).
+    cudaEvent_t ev_join = nullptr;
     if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly && !s.d_thresh_poly) {
-        // plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_fork = nullptr;
+        LSS_CUDA_CHECK(e, lss_side_stream(e, &side, &ev_fork, &ev_join));
+        LSS_CUDA_CHECK(e, cudaEventRecord(ev_fork, stream));            // after the offsets upload above
+        LSS_CUDA_CHECK(e, cudaStreamWaitEvent(side, ev_fork, 0));
         lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
-                                        nullptr, d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, stream);
-        if (ps != LSS_OK) return ps;
+                                        nullptr, d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, side);
+        const cudaError_t je = cudaEventRecord(ev_join, side);
+        if (ps != LSS_OK || je != cudaSuccess) {
+            cudaStreamWaitEvent(stream, ev_join, 0);                    // never leave the side stream dangling
+            return ps != LSS_OK ? ps : lss_fail(e, LSS_ERR_CUDA, "event record failed");
+        }
     }
 
     DevArgs a;
@@ -870,8 +957,9 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.att_cnt = d_att_cnt;
     a.att_sum = d_att_sum;
     a.status = e->d_status;
-    unsigned long long *d_ovf_list = (unsigned long long *)(ws + w.ovf + 256);
+    unsigned long long *d_ovf_list = (unsigned long long *)(ws + w.ovf + LIST_HDR_BYTES);
     unsigned long long *d_solve_list = d_ovf_list + OVF_LIST_CAP;
+    unsigned long long *d_sorted_list = d_solve_list + N;
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
         // 1. scan: all beams; the ones without occluders are finished, the others go to the solve list
@@ -880,14 +968,20 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
         k_snowfall<FAST_CAP, MODE_SCAN><<<grid, SNOW_TPB, 0, stream>>>(a);
         // 2. solve: the listed beams, densely packed (every lane has occluders); CTAs beyond the list exit at once
-        a.list_in = d_solve_list; a.count_in = d_counts2; a.cap_in = a.cap_out;
+        k_list_sort<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, a.cap_out);
+        a.list_in = d_sorted_list; a.count_in = d_counts2; a.cap_in = a.cap_out;
         a.list_out = d_ovf_list; a.count_out = d_counts2 + 1; a.cap_out = OVF_LIST_CAP;
         k_snowfall<FAST_CAP, MODE_LIST><<<(unsigned)((N + SNOW_TPB - 1) / SNOW_TPB), SNOW_TPB, 0, stream>>>(a);
         // 3. overflow: beams with more than FAST_CAP occluders (rare), redone with SLOW_CAP
         a.list_in = d_ovf_list; a.count_in = d_counts2 + 1; a.cap_in = OVF_LIST_CAP;
         a.list_out = nullptr; a.count_out = nullptr; a.cap_out = 0;
         k_snowfall<SLOW_CAP, MODE_LIST><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
-        e->launches += 2;
+        e->launches += 3;
+    }
+    if (ev_join) LSS_CUDA_CHECK(e, cudaStreamWaitEvent(stream, ev_join, 0));
+    {
+        KernelTimer kt(e, LSS_K_FINALIZE, stream);
+        k_keep<<<dim3(max_tiles, B), TILE, 0, stream>>>(a);
     }
     {
         KernelTimer kt(e, LSS_K_SORT, stream);
