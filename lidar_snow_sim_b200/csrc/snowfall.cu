@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
                 base = __shfl_sync(pm, base, leader);
                 // work class of the beam: everything it costs the solve kernel (bucket prefix, occluders, samples)
                 // grows with the target range
-                const int cls = min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
+                // grows with the target range; the costliest class comes first so that the kernel's tail is cheap CTAs
+                const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
                 a.list_out[base + __popc(pm & ((1u << lane) - 1u))] =
                     ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
                 const unsigned cm = __match_any_sync(pm, cls);
@@ -593,12 +594,15 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
 // (the warp runs as long as its slowest lane).  hdr: [0] entries, [LIST_CLASSES + c] class counts (from the scan kernel),
 // [2 * LIST_CLASSES + c] class cursors.  Order inside a class is arbitrary: the results do not depend on list order.
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int SORT_PER_THREAD = 8;
 __global__ void __launch_bounds__(256) k_list_sort(const unsigned long long *__restrict__ in, unsigned long long *out,
                                                     int *hdr, int cap)
 {
-    __shared__ int base[LIST_CLASSES];
+    __shared__ int base[LIST_CLASSES], hist[LIST_CLASSES], blk[LIST_CLASSES];
     const int cnt = min(hdr[0], cap);
-    if (blockIdx.x * 256 >= cnt) return;
+    const int first = blockIdx.x * (256 * SORT_PER_THREAD);
+    if (first >= cnt) return;
+    for (int c = threadIdx.x; c < LIST_CLASSES; c += 256) hist[c] = 0;
     if (threadIdx.x < 32) {                                  // exclusive scan of the class counts, one warp
         int run = 0;
         for (int c0 = 0; c0 < LIST_CLASSES; c0 += 32) {
@@ -614,16 +618,34 @@ __global__ void __launch_bounds__(256) k_list_sort(const unsigned long long *__r
         }
     }
     __syncthreads();
-    const int slot = blockIdx.x * 256 + threadIdx.x;
-    const bool on = slot < cnt;
-    const unsigned long long it = on ? in[slot] : 0ull;
-    const int cls = on ? (int)(it >> 48) : -1;
-    const unsigned m = __match_any_sync(0xffffffffu, cls);
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int pos = 0;
-    if (on && lane == leader) pos = atomicAdd(&hdr[2 * LIST_CLASSES + cls], __popc(m));
-    pos = __shfl_sync(0xffffffffu, pos, leader);
-    if (on) out[base[cls] + pos + __popc(m & ((1u << lane) - 1u))] = it;
+    // rank inside the block (shared-memory counters, warp-aggregated), then ONE global cursor update per class and
+    // block: the neighbouring beams of a cloud fall into few classes, per-entry global atomics would serialise
+    const int lane = threadIdx.x & 31;
+    unsigned long long it[SORT_PER_THREAD];
+    int rank[SORT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < SORT_PER_THREAD; k++) {
+        const int slot = first + k * 256 + threadIdx.x;
+        const bool on = slot < cnt;
+        it[k] = on ? in[slot] : ~0ull;
+        const int cls = on ? (int)(it[k] >> 48) : -1;
+        const unsigned m = __match_any_sync(0xffffffffu, cls);
+        const int leader = __ffs(m) - 1;
+        int r = 0;
+        if (on && lane == leader) r = atomicAdd(&hist[cls], __popc(m));
+        r = __shfl_sync(0xffffffffu, r, leader);
+        rank[k] = r + __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < LIST_CLASSES; c += 256)
+        blk[c] = hist[c] ? atomicAdd(&hdr[2 * LIST_CLASSES + c], hist[c]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_PER_THREAD; k++)
+        if (it[k] != ~0ull) {
+            const int cls = (int)(it[k] >> 48);
+            out[base[cls] + blk[cls] + rank[k]] = it[k];
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -968,7 +990,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
         k_snowfall<FAST_CAP, MODE_SCAN><<<grid, SNOW_TPB, 0, stream>>>(a);
         // 2. solve: the listed beams, densely packed (every lane has occluders); CTAs beyond the list exit at once
-        k_list_sort<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, a.cap_out);
+        k_list_sort<<<(unsigned)((N + 256 * SORT_PER_THREAD - 1) / (256 * SORT_PER_THREAD)), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, a.cap_out);
         a.list_in = d_sorted_list; a.count_in = d_counts2; a.cap_in = a.cap_out;
         a.list_out = d_ovf_list; a.count_out = d_counts2 + 1; a.cap_out = OVF_LIST_CAP;
         k_snowfall<FAST_CAP, MODE_LIST><<<(unsigned)((N + SNOW_TPB - 1) / SNOW_TPB), SNOW_TPB, 0, stream>>>(a);

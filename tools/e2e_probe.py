@@ -53,7 +53,7 @@ def main():
     res['inflight2'] = {}
     res['inflight3'] = {}
     hos = [{}, {}, {}]
-    for chunks in (1, 2, 4, 8):
+    for chunks in (1, 2, 3, 4):
         ho = hos[0]
         res['host'][str(chunks)] = timed(lambda: eng.snowfall_batch_host(tid, host, off, orders, bench.DIV_DEG, host_out=ho,
                                                                         device_prepass=True, n_chunks=chunks), reps=8)
