@@ -394,14 +394,16 @@ def main():
     k_avg_ms = k_ms / max(k_calls, 1)
     algo_bytes = ALGO_BYTES_PER_POINT * N + tinfo['bytes']
     achieved = algo_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'k_snowfall beam stage: scan <24,0> + solve <24,1> (dominant) + overflow <128,1> launches',
+    roofline = {'bound': 'hbm', 'kernel': 'k_snowfall beam stage: scan <24,0> + list sort + solve <24,1> (dominant) + overflow <128,1> launches',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': int(algo_bytes), 'kernel_ms': k_avg_ms,
                 'kernel_share_of_step': k_avg_ms / ms_per_step,
                 'kernel_ms_all': {k: (v[0] / max(v[1], 1)) * (v[1] / args.steps) for k, v in ktimes.items() if v[1]},
                 'note': 'latency / FP64-issue bound, not HBM bound (DESIGN.md 4, profiles/): duration = CUDA events around the '
-                        'three launches of the beam stage; traffic = their summed dram bytes from profiles/traffic.json'}
+                        'beam-stage launches while the pre-pass runs concurrently on a side stream (kernel_ms_all therefore '
+                        'sums to more than the step); traffic = summed dram bytes of the scan, solve and overflow launches '
+                        'from profiles/traffic.json'}
     prof = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(prof):
         try:
