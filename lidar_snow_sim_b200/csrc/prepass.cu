@@ -383,6 +383,7 @@ __device__ __forceinline__ GroundPt ground_point(const PreArgs &a, const CloudPr
     const double pw = lss_plane_dot(x, y, z, cp.w);                        // np.matmul(pc[:, :3], w)
     const double hgt = pw + cp.h;
     g.ground = (hgt < a.delta) && (hgt > -a.delta);                       // simulation.py:450-451
+    if (!g.ground) { g.d = 0.0; g.cosang = 0.0; g.norm_i = 0.0; return g; }   // callers only use ground points
     g.d = a.range64 ? sqrt((x * x + y * y) + z * z) : (double)range32(r[0], r[1], r[2]);
     double c;
     if (a.flat_earth) c = -(z) / (g.d * 1.0);                             // augmentation.py:61-63
@@ -391,7 +392,7 @@ __device__ __forceinline__ GroundPt ground_point(const PreArgs &a, const CloudPr
     // (augmentation.py:207, simulation.py:462): cos(arccos(c)) == c to 1 ulp for |c| <= 1 and NaN beyond, so the two
     // float64 transcendentals per ground point and pass are skipped (the pre-pass is parity-by-tolerance).
     g.cosang = (c >= -1.0 && c <= 1.0) ? c : __longlong_as_double(0x7ff8000000000000LL);
-    g.norm_i = g.ground ? (double)r[3] / g.cosang : 0.0;                  // augmentation.py:207
+    g.norm_i = (double)r[3] / g.cosang;                                   // augmentation.py:207
     return g;
 }
 
