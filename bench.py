@@ -248,6 +248,10 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
 
+    numa_cpus = None
+    if world > 1 and os.environ.get('LSS_NUMA_BIND'):     # opt-in: measured no consistent gain on the 2-GPU box
+        from lidar_snow_sim_b200.distributed import bind_host_to_gpu
+        numa_cpus = bind_host_to_gpu(local_rank)          # pinned host buffers land on the GPU's own NUMA node
     eng = SnowfallEngine(local_rank)
     tables = sample_table_set(MODE, SNOWFALL_RATE, TERMINAL_VELOCITY, seed=1000)
     tid = eng.upload_tables(tables)
@@ -377,6 +381,7 @@ def main():
                'd2h_bytes_per_step': int(N * 20 + B * 4 + B * 32), 'ms_per_step': dt * 1e3,
                'sync_call': {'value': points_all / dt_sync, 'ms_per_step': dt_sync * 1e3},
                'chunks': args.e2e_chunks, 'batches_in_flight': depth,
+               'host_numa_bound_cpus': None if numa_cpus is None else len(numa_cpus),
                'timing': 'host wall clock around K steps of the C-ABI host-buffer calls lss_snowfall_batch_host_submit / '
                          '_wait (pinned host in -> copy-in / pre-pass / beam / copy-out streams -> pinned host out), '
                          'with up to batches_in_flight steps submitted before the oldest is awaited; sync_call = the same batches '

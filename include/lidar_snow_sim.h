@@ -197,6 +197,37 @@ LSS_API lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, co
                                 void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_wet_ground_workspace_bytes(int64_t n_total, int n_clouds);
 
+/* ---- fog simulation ("next" row) -----------------------------------------------------------------------
+ * Batched simulate_fog() (lib/LiDAR_fog_sim/fog_simulation.py:299-316: P_R_fog_hard :183-189, P_R_fog_soft :192-296) on
+ * device-resident clouds of n_features (>= 4: x, y, z, intensity, ...) float32 columns.
+ *   alpha, beta, beta_0   the ParameterSet fields the reference reads (:66, :73, :168)
+ *   d_lut     float64[2001*2]  the integral look-up table the reference unpickles (get_integral_dict, :174-180) as
+ *                              (fog_distance, fog_response) per 0.1 m of range 0 .. 200 m; device memory
+ *   flags     LSS_FOG_HARD | LSS_FOG_SOFT | LSS_FOG_GAIN   (hard=, soft=, gain= of simulate_fog)
+ *   noise, noise_variant       `noise` (0: none) and 1..4 for 'v1'..'v4' (:237-266)
+ *   h_rng_state  uint64[n_clouds*4] or NULL: per cloud the PCG64 state {state_hi, state_lo, inc_hi, inc_lo} of the
+ *                caller's numpy Generator AFTER the one `integers` draw of :207.  Fog point number k of a cloud (in point
+ *                order) uses the generator's k-th next double, exactly like the reference's sequential draws; the
+ *                caller advances its generator by the returned count afterwards.  Used for variants 1-3.
+ *   d_ext_noise  float64[n_total] or NULL: externally drawn values by (cloud offset + rank) instead: uniforms in [0,1)
+ *                for variants 1-3, Generator.beta(2, 20) draws for variant 4 (rejection sampling cannot jump ahead:
+ *                call once without it to get ranks and counts, draw, call again).  Variant 4 without it: no noise.
+ *   d_out        float64[n_total*n_features]  augmented rows in input order (float32 valued when only LSS_FOG_HARD)
+ *   d_out_fog_mask uint8[n_total]             1 = the fog response replaced the return (simulated_fog_pc = rows with 1)
+ *   d_out_rank   int32[n_total] or NULL       rank of each fog point among its cloud's fog points, -1 elsewhere
+ *   d_out_info   float64[n_clouds*3]          min_fog_response (inf if none), max_fog_response, num_fog_responses
+ * Parity: masks, ranks, counts and the random stream are exact; intensities / coordinates agree to float64 rounding
+ * except where the reference itself is host-defined (float32 np.exp, scalar float32 power, pow): DESIGN.md 8.          */
+#define LSS_FOG_HARD 0x1u
+#define LSS_FOG_SOFT 0x2u
+#define LSS_FOG_GAIN 0x4u
+LSS_API lss_status lss_fog_batch(lss_engine *e, const float *d_points, int n_features, const int64_t *h_cloud_offsets,
+                                 int n_clouds, double alpha, double beta, double beta_0, const double *d_lut,
+                                 uint32_t flags, int noise, int noise_variant, const uint64_t *h_rng_state,
+                                 const double *d_ext_noise, double *d_out, uint8_t *d_out_fog_mask, int32_t *d_out_rank,
+                                 double *d_out_info, void *d_workspace, int64_t workspace_bytes, void *stream);
+LSS_API int64_t lss_fog_workspace_bytes(int64_t n_total, int n_clouds);
+
 /* ---- snowflake table sampler ---------------------------------------------------------------------------------------
  * dart_throwing(occupancy_ratio, precipitation_rate, R_0, rng, distribution) of tools/snowfall/sampling.py:90-194:
  * sequential rejection sampling of non-overlapping disks in a disk of radius R_0 until the occupied area reaches

@@ -25,6 +25,7 @@ FLAG_THRESHOLD_FILTER = 0x1
 FLAG_CAMERA_FOV = 0x2
 FLAG_DEVICE_PREPASS = 0x4
 FLAG_ASSUME_SORTED = 0x8
+FOG_HARD, FOG_SOFT, FOG_GAIN = 0x1, 0x2, 0x4
 
 # status -> exception type the reference would have raised at the corresponding place (SURVEY.md 8b "Errors")
 _EXC = {
@@ -73,6 +74,9 @@ SIGNATURES = [
     ('lss_wet_ground_batch', _c.c_int, [_P, _P, _P, _P, _c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_double,
                                         _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),
     ('lss_wet_ground_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
+    ('lss_fog_batch', _c.c_int, [_P, _P, _c.c_int, _P, _c.c_int, _c.c_double, _c.c_double, _c.c_double, _P, _c.c_uint32,
+                                 _c.c_int, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),
+    ('lss_fog_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
     ('lss_dart_throwing', _c.c_int, [_c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P, _c.c_int64,
                                      _c.POINTER(_c.c_int64)]),
     ('lss_dart_throwing_planes', _c.c_int, [_c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_int, _P, _P,

@@ -177,7 +177,7 @@ inline cudaError_t lss_zero_async(lss_engine *e, const ZeroRegions &r, cudaStrea
 }
 
 enum { LSS_K_SORT = 0, LSS_K_PREPASS = 1, LSS_K_SNOWFALL = 2, LSS_K_COMPACT = 3, LSS_K_FINALIZE = 4, LSS_K_WET = 5,
-       LSS_K_COUNT = 6 };
+       LSS_K_FOG = 6, LSS_K_COUNT = 7 };
 
 struct KernelTimer {        // RAII: records begin/end events when profiling is on
     lss_engine *e; cudaStream_t s; int idx = -1;

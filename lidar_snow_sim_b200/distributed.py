@@ -14,6 +14,32 @@ import torch
 import torch.distributed as dist
 
 
+def bind_host_to_gpu(device: int = 0):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (first-touch then places pinned host buffers
+    there), so that one rank's PCIe traffic does not cross the socket interconnect.  Call before allocating host
+    buffers.  Returns the cpu list used, or None when the topology cannot be read (no-op)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device)
+        pci = f'{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{pci}/local_cpulist') as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(','):
+            if '-' in part:
+                lo, hi = part.split('-')
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def shard_range(n_clouds: int, rank: int, world: int):
     """Contiguous block partition of cloud indices: rank r owns [start, stop)."""
     base, rem = divmod(n_clouds, world)

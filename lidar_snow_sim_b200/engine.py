@@ -325,6 +325,40 @@ class SnowfallEngine:
         _lib.check(st, self.h)
         return out
 
+    def fog_batch(self, points, cloud_offsets, lut, alpha, beta, beta_0, hard=True, soft=True, gain=False, noise=0,
+                  noise_variant=1, rng_states=None, ext_noise=None, want_rank=False):
+        """
+        Batched simulate_fog() (lib/LiDAR_fog_sim/fog_simulation.py:299-316) on device-resident clouds (current stream,
+        no synchronisation).  points: CUDA float32 (N, F), F >= 4; lut: CUDA float64 (2001, 2) integral look-up table;
+        rng_states: host uint64 (B, 4) PCG64 states (variants 1-3) or ext_noise: CUDA float64 (N,) values by rank.
+        Returns dict(points float64 (N, F), fog_mask uint8 (N,), info float64 (B, 3) [, rank int32 (N,)]).
+        """
+        off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
+        B = off.shape[0] - 1
+        N = int(off[-1])
+        assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.shape[0] == N
+        F = int(points.shape[1])
+        if lut is not None:
+            assert lut.is_cuda and lut.dtype == torch.float64 and lut.is_contiguous() and tuple(lut.shape) == (2001, 2)
+        rs = None if rng_states is None else np.ascontiguousarray(rng_states, dtype=np.uint64).reshape(B, 4)
+        if ext_noise is not None:
+            assert ext_noise.is_cuda and ext_noise.dtype == torch.float64 and ext_noise.numel() >= N
+        flags = (_lib.FOG_HARD if hard else 0) | (_lib.FOG_SOFT if soft else 0) | (_lib.FOG_GAIN if gain else 0)
+        with torch.cuda.device(self.device):
+            out = dict(points=torch.empty((N, F), dtype=torch.float64, device=self.device),
+                       fog_mask=torch.empty((N,), dtype=torch.uint8, device=self.device),
+                       info=torch.empty((B, 3), dtype=torch.float64, device=self.device))
+            if want_rank:
+                out['rank'] = torch.empty((N,), dtype=torch.int32, device=self.device)
+            need = self.lib.lss_fog_workspace_bytes(N, B)
+            ws = torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device)
+            st = self.lib.lss_fog_batch(self.h, _ptr(points), F, _ptr(off), B, float(alpha), float(beta), float(beta_0),
+                                        _ptr(lut), flags, int(noise), int(noise_variant), _ptr(rs), _ptr(ext_noise),
+                                        _ptr(out['points']), _ptr(out['fog_mask']), _ptr(out.get('rank')),
+                                        _ptr(out['info']), _ptr(ws), int(ws.numel()), self._stream())
+        _lib.check(st, self.h)
+        return out
+
     def check(self):
         """Synchronise the current stream and raise the exception type the reference would have raised."""
         with torch.cuda.device(self.device):
@@ -339,7 +373,7 @@ class SnowfallEngine:
     def kernel_times(self, reset=True):
         """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream (synchronises)."""
         torch.cuda.synchronize(self.device)
-        n = 6
+        n = 7
         ms = np.zeros(n, dtype=np.float64)
         calls = np.zeros(n, dtype=np.int64)
         _lib.check(self.lib.lss_kernel_times(self.h, 1 if reset else 0, _ptr(ms), _ptr(calls), n), self.h)
