@@ -18,6 +18,7 @@ on the device once per (mode, pair) and cached.
 import numpy as np
 
 from ..engine import default_engine
+from ..fog.simulation import ParameterSet, simulate_fog
 from ..snowfall.precompute import SNOWFALL_RATES, TERMINAL_VELOCITIES, get_fov_flag
 from ..snowfall.sampling import snowfall_rate_to_rainfall_rate
 from ..snowfall.simulation import augment
@@ -99,3 +100,24 @@ class OnTheFlyWeather:
                 except (TypeError, ValueError):                                        # dense_dataset.py:834-837
                     pass
         return points
+
+
+def foggify_cvl(points, alpha, dataset_cfg, engine=None, lut_dir=None, rng=None):
+    """The 'CVL' branch of `DenseDataset.foggify` (lib/OpenPCDet/pcdet/datasets/dense/dense_dataset.py:988-1009): fog
+    simulation with attenuation `alpha` (a string like '0.060' in the reference's curriculum; '0.000' = clear) and the
+    optional config keys FOG_GAIN / FOG_NOISE_VARIANT / FOG_SOFT / FOG_HARD, computed by the engine."""
+    if alpha == '0.000' or float(alpha) == 0.0:
+        return points
+    p = ParameterSet(alpha=float(alpha), gamma=0.000001)
+    soft, hard, gain, fog_noise_variant = True, True, False, 'v1'
+    if 'FOG_GAIN' in dataset_cfg:
+        gain = dataset_cfg['FOG_GAIN']
+    if 'FOG_NOISE_VARIANT' in dataset_cfg:
+        fog_noise_variant = dataset_cfg['FOG_NOISE_VARIANT']
+    if 'FOG_SOFT' in dataset_cfg:
+        soft = dataset_cfg['FOG_SOFT']
+    if 'FOG_HARD' in dataset_cfg:
+        hard = dataset_cfg['FOG_HARD']
+    points, _, _ = simulate_fog(p, pc=points, noise=10, gain=gain, noise_variant=fog_noise_variant, soft=soft, hard=hard,
+                                engine=engine, lut_dir=lut_dir, rng=rng)
+    return points

@@ -75,7 +75,21 @@ def precompute(sample_ids, lidar_folder, modes=('gunn', 'sekhon'), npy_root=None
                 continue
             tabs = sample_table_set(mode, rs, tv, seed=table_seed) if sample_tables else _load_tables(mode, rain, occ, npy_root)
             tid = engine.upload_tables(tabs, max_beam_divergence_rad=DEFAULT_MAX_DIVERGENCE_RAD)
+            def finish(job):
+                # wait for a submitted batch and write its files (precompute.py:105-106)
+                ticket, ids_j, off_j = job
+                res = engine.snowfall_batch_host_wait(ticket)
+                out = res['points'].numpy()
+                for b, s in enumerate(ids_j):
+                    out[off_j[b]:off_j[b] + int(res['counts'][b])].astype(np.float32).tofile(str(save_dir / f'{s}.bin'))
+                if progress:
+                    progress(mode, rain, len(ids_j))
+                return len(ids_j)
+
+            pending = None
             try:
+                # double buffered: while the GPU works on batch k, the host reads the files of batch k+1 and writes
+                # those of batch k-1
                 for i0 in range(0, len(todo), batch_frames):
                     ids = todo[i0:i0 + batch_frames]
                     clouds = []
@@ -90,15 +104,21 @@ def precompute(sample_ids, lidar_folder, modes=('gunn', 'sekhon'), npy_root=None
                             random.shuffle(o)                        # simulation.py:485-486
                         orders.append(o)
                     host = torch.from_numpy(np.concatenate(clouds)).pin_memory()
-                    res = engine.snowfall_batch_host(tid, host, off, np.asarray(orders, dtype=np.int32), div_deg,
-                                                     device_prepass=True, camera_fov=only_camera_fov,
-                                                     n_chunks=min(4, len(ids)))
-                    out = res['points'].numpy()
-                    for b, s in enumerate(ids):
-                        out[off[b]:off[b] + int(res['counts'][b])].astype(np.float32).tofile(str(save_dir / f'{s}.bin'))
-                        written += 1
-                    if progress:
-                        progress(mode, rain, len(ids))
+                    ticket = engine.snowfall_batch_host_submit(tid, host, off, np.asarray(orders, dtype=np.int32), div_deg,
+                                                               device_prepass=True, camera_fov=only_camera_fov,
+                                                               n_chunks=min(4, len(ids)))
+                    if pending is not None:
+                        job, pending = pending, None
+                        written += finish(job)
+                    pending = (ticket, ids, off)
+                if pending is not None:
+                    job, pending = pending, None
+                    written += finish(job)
             finally:
+                if pending is not None:                              # an exception above: do not leave a batch in flight
+                    try:
+                        engine.snowfall_batch_host_wait(pending[0])
+                    except Exception:
+                        pass
                 engine.free_tables(tid)
     return written

@@ -147,3 +147,24 @@ def test_full_size_and_errors(engine, gold):
     from lidar_snow_sim_b200.fog import simulate_fog
     with pytest.raises(NotImplementedError):                                              # fog_simulation.py:264-266
         simulate_fog(p, clouds[0][:100], 10, noise_variant='v9', engine=engine, lut=gold['lut_0.2'])
+
+
+def test_foggify_cvl_from_pickled_tables(engine, gold, tmp_path):
+    """The DenseDataset.foggify 'CVL' branch through the table loader: pickles in the reference's file layout."""
+    import pickle
+    from lidar_snow_sim_b200.fog import ParameterSet, simulate_fog
+    from lidar_snow_sim_b200.integrations.dense import foggify_cvl
+    for a in (0.06, 0.2):
+        lut = gold[f'lut_{a}']
+        d = {round(i * 0.1, 2): (np.float64(lut[i, 0]), np.float64(lut[i, 1])) for i in range(2001)}
+        (tmp_path / f'integral_0m_to_200m_stepsize_0.1m_tau_h_20ns_alpha_{a}.pickle').write_bytes(pickle.dumps(d))
+    pc = gold['pc']
+    got = foggify_cvl(pc, '0.200', {'FOG_NOISE_VARIANT': 'v2', 'FOG_GAIN': True}, engine=engine, lut_dir=tmp_path,
+                      rng=np.random.default_rng(42))
+    want, _, _ = simulate_fog(ParameterSet(alpha=0.2, gamma=0.000001), pc, 10, gain=True, noise_variant='v2',
+                              engine=engine, lut=gold['lut_0.2'], rng=np.random.default_rng(42))
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    assert foggify_cvl(pc, '0.000', {}, engine=engine) is pc
+    hard_only = foggify_cvl(pc, '0.060', {'FOG_SOFT': False}, engine=engine, lut_dir=tmp_path)
+    assert hard_only.dtype == np.float32 and np.array_equal(hard_only[:, :3], pc[:, :3])
+    assert np.all(hard_only[:, 3] <= pc[:, 3])
