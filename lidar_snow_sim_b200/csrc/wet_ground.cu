@@ -3,8 +3,9 @@
 //   pre-pass (prepass.cu)   plane, ground band |p.w + h| < delta, incident angle, estimate_laser_parameters
 //   k_wet_points            per ground point: reflectivity, two Fresnel interfaces air->water->ground->water->air
 //                           (tools/wet_ground/phy_equations.py:35-108), wet/dry mixing, clipped new intensity, drop test
-//   k_wet_compact           output order of the reference: all non-ground rows first, then the kept ground rows
-//                           (augmentation.py:150-159), column 4 rewritten
+//   k_wet_tile_count / k_wet_tile_scan / k_wet_scatter
+//                           output order of the reference: all non-ground rows first, then the kept ground rows
+//                           (augmentation.py:150-159), column 4 rewritten; stable, tile parallel
 //
 // All per-point physics in float64, as the reference (its ground array is float64, augmentation.py:50).
 // A cloud with fewer than 1000 ground points is passed through unchanged (augmentation.py:51-52).
@@ -27,6 +28,9 @@ struct WetArgs {
     double *out_i64;              // optional [N] float64 intensity of the output rows
     int32_t *out_counts;          // [B]
     int32_t *out_passthrough;     // [B] 1 = cloud returned unchanged
+    const int32_t *tile_base;     // [B+1] tiles of 1024 rows per cloud slot
+    int *tile_cnt;                // [tiles*2] rows of class 0 / class 1 per tile
+    int *tile_off;                // [tiles*2] exclusive scans per cloud
 };
 
 struct Fresnel { double rs, ts, rp, tp, aout; };
@@ -96,56 +100,110 @@ __global__ void __launch_bounds__(WET_TPB) k_wet_points(WetArgs a)
     }
 }
 
-// one CTA per cloud: stable two-stream compaction [not ground ...][kept ground ...]
-__global__ void __launch_bounds__(1024) k_wet_compact(WetArgs a)
+// Stable two-stream compaction [not ground ...][kept ground ...] (augmentation.py:150-153), tile parallel:
+//   k_wet_tile_count   per tile of 1024 points: rows of class 0 (not ground) and class 1 (ground kept)
+//   k_wet_tile_scan    per cloud: exclusive scan of both tile counts, output count, pass-through flag
+//   k_wet_scatter      per tile: destination = stream base + tile offset + rank inside the tile
+constexpr int WET_TILE = 1024;
+
+__global__ void __launch_bounds__(WET_TILE) k_wet_tile_count(WetArgs a)
+{
+    __shared__ int ca, cb;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int n = cloud_n(a, b);
+    if (tile * WET_TILE >= n) {
+        if (threadIdx.x == 0 && tile < a.tile_base[b + 1] - a.tile_base[b]) {
+            a.tile_cnt[2 * (a.tile_base[b] + tile)] = 0;              // tile of the slot beyond the valid rows
+            a.tile_cnt[2 * (a.tile_base[b] + tile) + 1] = 0;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    const int i = tile * WET_TILE + threadIdx.x;
+    const int c = i < n ? a.cls[a.cloud_off[b] + i] : 3;
+    const unsigned ma = __ballot_sync(0xffffffffu, c == 0), mb = __ballot_sync(0xffffffffu, c == 1);
+    if ((threadIdx.x & 31) == 0) {
+        if (ma) atomicAdd(&ca, __popc(ma));
+        if (mb) atomicAdd(&cb, __popc(mb));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.tile_cnt[2 * (a.tile_base[b] + tile)] = ca;
+        a.tile_cnt[2 * (a.tile_base[b] + tile) + 1] = cb;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_wet_tile_scan(WetArgs a)
 {
     __shared__ int wa[32], wb[32];
     __shared__ int run_a, run_b;
     const int b = blockIdx.x;
-    const CloudPre &cp = a.cp[b];
-    const int64_t beg = a.cloud_off[b];
-    const int n = cloud_n(a, b);
-    const bool pass = cp.n_ground < 1000;
-    const int n_non = pass ? n : n - cp.n_ground;
+    const int t0 = a.tile_base[b], nt = a.tile_base[b + 1] - t0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { run_a = 0; run_b = 0; }
     __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += 1024) {
-        const int i = t0 + tid;
-        const int c = i < n ? a.cls[beg + i] : 3;
-        const unsigned ma = __ballot_sync(0xffffffffu, c == 0), mb = __ballot_sync(0xffffffffu, c == 1);
-        if (lane == 0) { wa[warp] = __popc(ma); wb[warp] = __popc(mb); }
+    for (int base = 0; base < nt; base += 1024) {
+        const int t = base + tid;
+        const int va = t < nt ? a.tile_cnt[2 * (t0 + t)] : 0, vb = t < nt ? a.tile_cnt[2 * (t0 + t) + 1] : 0;
+        int ia = va, ib = vb;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int ua = __shfl_up_sync(0xffffffffu, ia, s), ub = __shfl_up_sync(0xffffffffu, ib, s);
+            if (lane >= s) { ia += ua; ib += ub; }
+        }
+        if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
         __syncthreads();
         int oa = run_a, ob = run_b;
         for (int wv = 0; wv < warp; wv++) { oa += wa[wv]; ob += wb[wv]; }
-        if (c == 0 || c == 1) {
-            const float *s = a.pts + (beg + i) * 5;
-            const int dst = (c == 0) ? oa + __popc(ma & ((1u << lane) - 1u))
-                                     : n_non + ob + __popc(mb & ((1u << lane) - 1u));
-            float *o = a.out + (beg + dst) * 5;
-            o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-            const double inten = (c == 1) ? a.new_i[beg + i] : (double)s[3];
-            o[3] = (float)inten;
-            o[4] = pass ? s[4] : ((c == 1) ? 1.0f : (a.replace ? 0.0f : s[4]));                 // :155-159
-            if (a.out_i64) a.out_i64[beg + dst] = inten;
+        if (t < nt) {
+            a.tile_off[2 * (t0 + t)] = oa + ia - va;
+            a.tile_off[2 * (t0 + t) + 1] = ob + ib - vb;
         }
         __syncthreads();
-        if (tid == 0) {
-            int ta = 0, tb = 0;
-            for (int wv = 0; wv < 32; wv++) { ta += wa[wv]; tb += wb[wv]; }
-            run_a += ta; run_b += tb;
-        }
+        if (tid == 1023) { run_a = oa + ia; run_b = ob + ib; }
         __syncthreads();
     }
     if (tid == 0) {
         a.out_counts[b] = run_a + run_b;
-        if (a.out_passthrough) a.out_passthrough[b] = pass ? 1 : 0;
+        if (a.out_passthrough) a.out_passthrough[b] = (a.cp[b].n_ground < 1000) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(WET_TILE) k_wet_scatter(WetArgs a)
+{
+    __shared__ int wa[WET_TILE / 32], wb[WET_TILE / 32];
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int n = cloud_n(a, b);
+    if (tile * WET_TILE >= n) return;
+    const CloudPre &cp = a.cp[b];
+    const int64_t beg = a.cloud_off[b];
+    const bool pass = cp.n_ground < 1000;
+    const int n_non = pass ? n : n - cp.n_ground;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = tile * WET_TILE + tid;
+    const int c = i < n ? a.cls[beg + i] : 3;
+    const unsigned ma = __ballot_sync(0xffffffffu, c == 0), mb = __ballot_sync(0xffffffffu, c == 1);
+    if (lane == 0) { wa[warp] = __popc(ma); wb[warp] = __popc(mb); }
+    __syncthreads();
+    if (c == 0 || c == 1) {
+        int oa = a.tile_off[2 * (a.tile_base[b] + tile)], ob = a.tile_off[2 * (a.tile_base[b] + tile) + 1];
+        for (int wv = 0; wv < warp; wv++) { oa += wa[wv]; ob += wb[wv]; }
+        const float *s = a.pts + (beg + i) * 5;
+        const int dst = (c == 0) ? oa + __popc(ma & ((1u << lane) - 1u))
+                                 : n_non + ob + __popc(mb & ((1u << lane) - 1u));
+        float *o = a.out + (beg + dst) * 5;
+        o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+        const double inten = (c == 1) ? a.new_i[beg + i] : (double)s[3];
+        o[3] = (float)inten;
+        o[4] = pass ? s[4] : ((c == 1) ? 1.0f : (a.replace ? 0.0f : s[4]));                 // :155-159
+        if (a.out_i64) a.out_i64[beg + dst] = inten;
     }
 }
 
 inline int64_t align_up(int64_t v, int64_t al) { return (v + al - 1) / al * al; }
 
-struct WetLayout { int64_t off, cls, new_i, prepass, prepass_bytes, total; };
+struct WetLayout { int64_t off, cls, new_i, tile_base, tile_cnt, tile_off, prepass, prepass_bytes, total; };
 
 WetLayout wet_layout(int64_t n_total, int n_clouds)
 {
@@ -154,6 +212,10 @@ WetLayout wet_layout(int64_t n_total, int n_clouds)
     L.off = o;      o = align_up(o + (int64_t)(n_clouds + 1) * 8, 256);
     L.cls = o;      o = align_up(o + n_total, 256);
     L.new_i = o;    o = align_up(o + n_total * 8, 256);
+    const int64_t tiles = n_total / 1024 + n_clouds + 1;
+    L.tile_base = o; o = align_up(o + (int64_t)(n_clouds + 1) * 4, 256);
+    L.tile_cnt = o;  o = align_up(o + tiles * 2 * 4, 256);
+    L.tile_off = o;  o = align_up(o + tiles * 2 * 4, 256);
     L.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     L.prepass = o;  o = align_up(o + L.prepass_bytes, 256);
     L.total = o;
@@ -229,7 +291,20 @@ lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int6
         a.out_counts = d_out_counts;
         a.out_passthrough = d_out_passthrough;
         int64_t max_n = 0;
-        for (int b = 0; b < B; b++) max_n = std::max<int64_t>(max_n, h_cloud_offsets[b + 1] - h_cloud_offsets[b]);
+        std::vector<int32_t> h_tb(B + 1, 0);
+        for (int b = 0; b < B; b++) {
+            const int64_t nb = h_cloud_offsets[b + 1] - h_cloud_offsets[b];
+            max_n = std::max<int64_t>(max_n, nb);
+            h_tb[b + 1] = h_tb[b] + (int32_t)((nb + WET_TILE - 1) / WET_TILE);
+        }
+        if (lss_stage_upload(e, ws + L.tile_base, h_tb.data(), sizeof(int32_t) * (B + 1), st) != cudaSuccess) {
+            rc = lss_fail(e, LSS_ERR_CUDA, "upload failed");
+            break;
+        }
+        a.tile_base = (const int32_t *)(ws + L.tile_base);
+        a.tile_cnt = (int *)(ws + L.tile_cnt);
+        a.tile_off = (int *)(ws + L.tile_off);
+        const int max_tiles = (int)std::max<int64_t>(1, (max_n + WET_TILE - 1) / WET_TILE);
         const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (max_n + WET_TPB * 4 - 1) / (WET_TPB * 4)));
         {
             KernelTimer kt(e, LSS_K_WET, st);
@@ -237,7 +312,10 @@ lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int6
         }
         {
             KernelTimer kt(e, LSS_K_COMPACT, st);
-            k_wet_compact<<<B, 1024, 0, st>>>(a);
+            k_wet_tile_count<<<dim3(max_tiles, B), WET_TILE, 0, st>>>(a);
+            k_wet_tile_scan<<<B, 1024, 0, st>>>(a);
+            k_wet_scatter<<<dim3(max_tiles, B), WET_TILE, 0, st>>>(a);
+            e->launches += 2;
         }
         if (cudaGetLastError() != cudaSuccess) rc = lss_fail(e, LSS_ERR_CUDA, "wet-ground launch failed");
     } while (0);
