@@ -108,6 +108,9 @@ LSS_API lss_status lss_table_info(lss_engine *e, int table_id, int64_t *n_partic
  *                                         device as the correctly rounded float32 of the float64 atan2.
  *   h_thresh_poly    float64[n_clouds*3] or NULL: np.polyfit coefficients p of simulation.py:467-469 per cloud
  *                                         (required with LSS_FLAG_THRESHOLD_FILTER unless LSS_FLAG_DEVICE_PREPASS)
+ *   h_plane_in       float64[n_clouds*4] or NULL, h_ymins_in int32[n_clouds*50] or NULL: with LSS_FLAG_DEVICE_PREPASS,
+ *                                         the two library-defined choices of the reference's pre-pass replayed from a
+ *                                         reference run (see lss_noise_threshold_poly); NULL = the device's own choice
  *   noise_floor                           simulation.py:428 (used by the device pre-pass only)
  *   flags                                 LSS_FLAG_*
  *   d_out_points     float32[n_total*5]   augmented rows (x, y, z, intensity, label), sorted by channel (stable), cloud b
@@ -125,7 +128,8 @@ LSS_API lss_status lss_table_info(lss_engine *e, int table_id, int64_t *n_partic
  * lss_check_async() after the stream has been synchronised by the caller.                                          */
 LSS_API lss_status lss_snowfall_batch(lss_engine *e, int table_id, const float *d_points, const int64_t *h_cloud_offsets,
                               int n_clouds, const int32_t *h_order, double beam_divergence_deg, const float *d_theta,
-                              const double *h_thresh_poly, double noise_floor, uint32_t flags, float *d_out_points,
+                              const double *h_thresh_poly, const double *h_plane_in, const int32_t *h_ymins_in,
+                              double noise_floor, uint32_t flags, float *d_out_points,
                               int32_t *d_out_counts, double *d_out_stats, float *d_out_full, int32_t *d_out_perm,
                               int32_t *d_out_nocc, void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_snowfall_workspace_bytes(int64_t n_total, int n_clouds);
@@ -168,11 +172,23 @@ LSS_API int64_t lss_launch_count(const lss_engine *e);
  * degree-2 noise-threshold polynomial (simulation.py:462-467) for every cloud of a batch.  lss_snowfall_batch runs
  * the same code with LSS_FLAG_DEVICE_PREPASS; this entry point exposes the results.
  *   h_plane_in   float64[n_clouds*4] (w0, w1, w2, h) or NULL.  NULL: estimated on the device (deterministic RANSAC).
+ *                The reference's plane comes from sklearn's RANSAC on NumPy's global RNG (planes.py:35).
+ *   h_ymins_in   int32[n_clouds*50] or NULL: per cloud and range bin, the intensity-bin index the reference host picked
+ *                with np.argpartition(hist, 2, axis=1)[:, 0] (augmentation.py:236) -- an implementation-defined one of the
+ *                least populated bins (AVX-512 / AVX2 / scalar NumPy builds pick differently).  NULL: the device takes the
+ *                FIRST least populated bin (NumPy's portable introselect).  With both inputs replayed from a reference
+ *                run everything downstream is comparable with that run's outputs (tests/golden/).
  *   d_poly_out   float64[n_clouds*3]  np.polyfit order (highest power first), device
- *   d_plane_out  float64[n_clouds*4] or NULL, device                                                                   */
+ *   d_plane_out  float64[n_clouds*4] or NULL, device
+ *   d_fit_out    float64[n_clouds*8] or NULL, device: linregress slope, intercept of I/cos over range
+ *                (augmentation.py:216-219); slope, intercept of the per-bin minima fit (:249); ymax (:233); n_ground;
+ *                points in the mounting window (planes.py:21-27); 1 if the flat-earth fallback was taken (:29-32)
+ *   d_ymins_out  int32[n_clouds*50] or NULL, device: the picks used (-1: fewer than 3 ground points)                    */
 LSS_API lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets,
-                                    int n_clouds, double noise_floor, const double *h_plane_in, double *d_poly_out,
-                                    double *d_plane_out, void *d_workspace, int64_t workspace_bytes, void *stream);
+                                    int n_clouds, double noise_floor, const double *h_plane_in,
+                                    const int32_t *h_ymins_in, double *d_poly_out, double *d_plane_out,
+                                    double *d_fit_out, int32_t *d_ymins_out, void *d_workspace,
+                                    int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds);
 
 /* ---- wet-ground augmentation ------------------------------------------------------------------------------------------
@@ -183,6 +199,7 @@ LSS_API int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds);
  *                     lss_snowfall_batch (fused snow -> wet path); NULL: h_cloud_offsets[b+1] - h_cloud_offsets[b]
  *   water_height, pavement_depth, noise_floor, power_factor, flat_earth, delta, replace: as in the reference signature
  *   h_plane_in        float64[n_clouds*4] (w0, w1, w2, h) or NULL (device RANSAC, planes.py:12-50)
+ *   h_ymins_in        int32[n_clouds*50] or NULL: replayed np.argpartition picks, see lss_noise_threshold_poly
  *   d_out_points      float32[n_total*5]: per cloud, non-ground rows first, then the kept ground rows (:150-159),
  *                     compacted to the front of the cloud's slot
  *   d_out_intensity64 float64[n_total] or NULL: column 3 of the output rows in the reference's float64
@@ -192,9 +209,9 @@ LSS_API int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds);
 LSS_API lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets,
                                 const int32_t *d_cloud_counts, int n_clouds, double water_height, double pavement_depth,
                                 double noise_floor, double power_factor, int flat_earth, double delta, int replace,
-                                const double *h_plane_in, float *d_out_points, double *d_out_intensity64,
-                                int32_t *d_out_counts, int32_t *d_out_passthrough, double *d_out_plane,
-                                void *d_workspace, int64_t workspace_bytes, void *stream);
+                                const double *h_plane_in, const int32_t *h_ymins_in, float *d_out_points,
+                                double *d_out_intensity64, int32_t *d_out_counts, int32_t *d_out_passthrough,
+                                double *d_out_plane, void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_wet_ground_workspace_bytes(int64_t n_total, int n_clouds);
 
 /* ---- fog simulation ("next" row) -----------------------------------------------------------------------

@@ -57,7 +57,7 @@ SIGNATURES = [
     ('lss_free_particles', _c.c_int, [_P, _c.c_int]),
     ('lss_table_info', _c.c_int, [_P, _c.c_int, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64),
                                   _c.POINTER(_c.c_int64)]),
-    ('lss_snowfall_batch', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_double, _P, _P, _c.c_double,
+    ('lss_snowfall_batch', _c.c_int, [_P, _c.c_int, _P, _P, _c.c_int, _P, _c.c_double, _P, _P, _P, _P, _c.c_double,
                                       _c.c_uint32, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),
     ('lss_snowfall_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
     ('lss_host_pipe_trace', _c.c_int, [_P, _P, _c.c_int]),
@@ -69,10 +69,11 @@ SIGNATURES = [
     ('lss_check_async', _c.c_int, [_P, _P]),
     ('lss_launch_count', _c.c_int64, [_P]),
     ('lss_debug_range_grid', _c.c_int, [_P]),
-    ('lss_noise_threshold_poly', _c.c_int, [_P, _P, _P, _c.c_int, _c.c_double, _P, _P, _P, _P, _c.c_int64, _P]),
+    ('lss_noise_threshold_poly', _c.c_int, [_P, _P, _P, _c.c_int, _c.c_double, _P, _P, _P, _P, _P, _P, _P, _c.c_int64,
+                                            _P]),
     ('lss_prepass_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
     ('lss_wet_ground_batch', _c.c_int, [_P, _P, _P, _P, _c.c_int, _c.c_double, _c.c_double, _c.c_double, _c.c_double,
-                                        _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),
+                                        _c.c_int, _c.c_double, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),
     ('lss_wet_ground_workspace_bytes', _c.c_int64, [_c.c_int64, _c.c_int]),
     ('lss_fog_batch', _c.c_int, [_P, _P, _c.c_int, _P, _c.c_int, _c.c_double, _c.c_double, _c.c_double, _P, _c.c_uint32,
                                  _c.c_int, _c.c_int, _P, _P, _P, _P, _P, _P, _P, _c.c_int64, _P]),

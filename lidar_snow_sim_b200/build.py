@@ -13,8 +13,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liblss_b200.so')
-SOURCES = ['api.cu', 'tables.cu', 'snowfall.cu', 'prepass.cu', 'wet_ground.cu', 'sampler.cu', 'sampler_gpu.cu', 'host_pipeline.cu', 'fog.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+SOURCES = ['api.cu', 'tables.cu', 'snowfall.cu', 'solve.cu', 'prepass.cu', 'wet_ground.cu', 'sampler.cu', 'sampler_gpu.cu', 'host_pipeline.cu', 'fog.cu']
+# -fmad=false: float32/float64 expressions are evaluated as written (mul, then add), like NumPy on the reference host;
+# where a fused multiply-add is wanted the source says fma() / __fma_rn() explicitly.
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-fmad=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-ffp-contract=off', '--shared', '-cudart', 'static']
 
 
@@ -29,14 +31,38 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'lidar_snow_sim.h')]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.startswith('_')] + [__file__] + [os.path.join(HERE, '..', 'include', 'lidar_snow_sim.h')]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False, extra=()):
+    """Compile every translation unit (in parallel, objects under csrc/_obj/) and link the shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra) + ['-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    objdir = os.path.join(CSRC, '_obj')
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ('--shared',)]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    headers.append(os.path.join(HERE, '..', 'include', 'lidar_snow_sim.h'))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+        path = os.path.join(CSRC, src)
+        if (not force and not extra and os.path.exists(obj) and
+                os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header, os.path.getmtime(__file__))):
+            return obj
+        cmd = [nvcc] + compile_flags + list(extra) + ['-c', '-o', obj, path]
+        if verbose:
+            print(' '.join(cmd))
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB] + objs
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

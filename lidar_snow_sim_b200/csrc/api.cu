@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -14,6 +15,20 @@ void host_range_grid(double *R)
     for (int k = 0; k < LSS_M_EXT; k++) {
         double v = (k == LSS_M_EXT - 1) ? stop : k * step;
         R[k] = std::nearbyint(v * 100.0) / 100.0;
+    }
+}
+
+// (sin, cos) of pi * R[k] / (c tau) for the solve kernel's angle-addition form of sin(pi (R_k - r) / (c tau))
+// (simulation.py:549).  Quotient, reduction modulo 2 and the functions themselves in long double (64-bit mantissa on
+// x86-64), so every entry is the correctly rounded double up to ~1e-19.
+void host_phase_table(const double *R, double *tab /* [2 * LSS_M_EXT] */)
+{
+    const long double ctau = (long double)(299792458.0 * 1e-8);       // the reference's float64 product c * tau_h
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int k = 0; k < LSS_M_EXT; k++) {
+        const long double a = fmodl((long double)R[k] / ctau, 2.0L);
+        tab[2 * k] = (double)sinl(pi * a);
+        tab[2 * k + 1] = (double)cosl(pi * a);
     }
 }
 
@@ -54,8 +69,16 @@ lss_status lss_create(int device, lss_engine **out)
     DeviceGuard g(device);
     double R[LSS_M_EXT];
     host_range_grid(R);
+    std::vector<double> wtab(2 * LSS_M_EXT);
+    host_phase_table(R, wtab.data());
     int zero = 0;
+    cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (e->n_sm <= 0) e->n_sm = 148;
+    const char *old = getenv("LSS_OLD_SOLVE");
+    e->old_solve = old && old[0] == '1';
     if (cudaMalloc(&e->d_R, sizeof(R)) != cudaSuccess || cudaMalloc(&e->d_status, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&e->d_wtab, sizeof(double) * wtab.size()) != cudaSuccess ||
+        cudaMemcpy(e->d_wtab, wtab.data(), sizeof(double) * wtab.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc(&e->d_sensor, sizeof(SensorConst)) != cudaSuccess ||
         cudaMalloc(&e->d_camera, sizeof(CameraConst)) != cudaSuccess ||
         cudaMemcpy(e->d_R, R, sizeof(R), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -77,6 +100,7 @@ void lss_destroy(lss_engine *e)
         cudaFree(kv.second.d_bucket_start);
     }
     cudaFree(e->d_R);
+    cudaFree(e->d_wtab);
     cudaFree(e->d_status);
     cudaFree(e->d_sensor);
     cudaFree(e->d_camera);
@@ -213,7 +237,8 @@ int64_t lss_snowfall_workspace_bytes(int64_t n_total, int n_clouds) { return lss
 
 lss_status lss_snowfall_batch(lss_engine *e, int table_id, const float *d_points, const int64_t *h_cloud_offsets,
                               int n_clouds, const int32_t *h_order, double beam_divergence_deg, const float *d_theta,
-                              const double *h_thresh_poly, double noise_floor, uint32_t flags, float *d_out_points,
+                              const double *h_thresh_poly, const double *h_plane_in, const int32_t *h_ymins_in,
+                              double noise_floor, uint32_t flags, float *d_out_points,
                               int32_t *d_out_counts, double *d_out_stats, float *d_out_full, int32_t *d_out_perm,
                               int32_t *d_out_nocc, void *d_workspace, int64_t workspace_bytes, void *stream)
 {
@@ -235,6 +260,8 @@ lss_status lss_snowfall_batch(lss_engine *e, int table_id, const float *d_points
     a.beam_divergence_deg = beam_divergence_deg;
     a.d_theta = d_theta;
     a.h_thresh_poly = h_thresh_poly;
+    a.h_plane_in = h_plane_in;
+    a.h_ymins_in = h_ymins_in;
     a.noise_floor = noise_floor;
     a.flags = flags;
     a.d_out_points = d_out_points;
@@ -255,8 +282,9 @@ int64_t lss_prepass_workspace_bytes(int64_t n_total, int n_clouds)
 }
 
 lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets, int n_clouds,
-                                    double noise_floor, const double *h_plane_in, double *d_poly_out,
-                                    double *d_plane_out, void *d_workspace, int64_t workspace_bytes, void *stream)
+                                    double noise_floor, const double *h_plane_in, const int32_t *h_ymins_in,
+                                    double *d_poly_out, double *d_plane_out, double *d_fit_out, int32_t *d_ymins_out,
+                                    void *d_workspace, int64_t workspace_bytes, void *stream)
 {
     if (!e) return LSS_ERR_INVALID_ARG;
     if (!d_points || !h_cloud_offsets || n_clouds <= 0 || !d_poly_out || !d_workspace)
@@ -269,8 +297,15 @@ lss_status lss_noise_threshold_poly(lss_engine *e, const float *d_points, const 
         return lss_fail(e, LSS_ERR_WORKSPACE, "workspace too small");
     int64_t *d_off = (int64_t *)d_workspace;
     LSS_CUDA_CHECK(e, lss_stage_upload(e, d_off, h_cloud_offsets, sizeof(int64_t) * (n_clouds + 1), st));
-    return lss_prepass_run(e, d_points, d_off, nullptr, h_cloud_offsets, n_clouds, 0.5, noise_floor, 0, 0, 1, h_plane_in, d_poly_out,
-                           d_plane_out, (char *)d_workspace + off_bytes, workspace_bytes - off_bytes, nullptr, st);
+    PrepassIO io;
+    io.h_plane_in = h_plane_in;
+    io.h_ymins_in = h_ymins_in;
+    io.d_poly_out = d_poly_out;
+    io.d_plane_out = d_plane_out;
+    io.d_fit_out = d_fit_out;
+    io.d_ymins_out = d_ymins_out;
+    return lss_prepass_run(e, d_points, d_off, nullptr, h_cloud_offsets, n_clouds, 0.5, noise_floor, 0, 0, 1, io,
+                           (char *)d_workspace + off_bytes, workspace_bytes - off_bytes, nullptr, st);
 }
 
 lss_status lss_check_async(lss_engine *e, void *stream)
@@ -299,7 +334,8 @@ lss_status lss_set_profiling(lss_engine *e, int enable)
     return LSS_OK;
 }
 
-static const char *kernel_names[LSS_K_COUNT] = {"channel_sort", "prepass", "snowfall", "compact", "keep", "wet_ground", "fog"};
+static const char *kernel_names[LSS_K_COUNT] = {"channel_sort", "prepass", "snowfall", "compact", "keep", "wet_ground", "fog",
+                                                "snowfall_scan", "snowfall_solve"};
 
 const char *lss_kernel_name(int kernel) { return (kernel >= 0 && kernel < LSS_K_COUNT) ? kernel_names[kernel] : ""; }
 

@@ -1,0 +1,115 @@
+// beam.cuh -- argument block, constants and small device helpers shared by the per-beam kernels
+// (snowfall.cu: scan / overflow / keep / scatter; solve.cu: the dense solve kernel).
+#pragma once
+#include "common.cuh"
+
+// argument block of the per-beam kernels (global type: it crosses translation units)
+struct DevArgs {
+    // tables
+    const ParticleRec *rec;
+    const BroadEntry *entries;
+    const int32_t *bucket_start;
+    int n_buckets;
+    int n_planes;
+    double inv_w, w;
+    // per call
+    const float *pts;            // rows in input order
+    const float *theta;          // optional, input order
+    const int64_t *cloud_off;    // [B+1] device
+    const int32_t *order;        // [B*64] device
+    const double *thresh;        // [B*3] device or null
+    const SensorConst *sensor;
+    const CameraConst *camera;
+    const double *R;
+    const double2 *wtab;         // [1230] (sin, cos) of pi * R[k] / (c tau): waveform phase table of the solve kernel
+    double half_div;             // radians(beam_divergence / 2)
+    double div_rad;              // radians(beam_divergence)
+    uint32_t flags;
+    float *aug;                  // [N*5] augmented rows, input order
+    uint8_t *code_keep;          // [N] channel bin of a kept row, 255 = dropped
+    uint8_t *code_all;           // optional [N] channel bin of every row (un-filtered debug output)
+    int32_t *nocc;               // optional [N], input order
+    unsigned *hist_keep;         // [sum of tiles * NBINS]; cloud b owns rows tile_base[b] .. tile_base[b+1]
+    unsigned *hist_all;          // optional
+    const int32_t *tile_base;    // [B+1] device
+    double *stats;               // [B*4]: num_attenuated, num_removed, avg_diff, diff_sum
+    int *counters;               // [B*2]: num_attenuated (threshold-kept), num_removed
+    unsigned *att_cnt;           // [B*64] label-1 beams per channel (all of them, simulation.py:170)
+    unsigned long long *att_sum; // [B] sum of their new integer intensities
+    int *status;
+    // work lists (cloud << 32 | row): the scan kernel defers every beam that has occluders to the dense solve kernel,
+    // which in turn defers beams with more than FAST_CAP occluders to the overflow kernel
+    const unsigned long long *list_in;
+    const int *count_in;
+    int cap_in;
+    unsigned long long *list_out;
+    int *count_out;
+    int cap_out;
+};
+
+namespace {
+
+constexpr int SNOW_TPB = 128;
+constexpr int SNOW_WARPS = SNOW_TPB / 32;
+constexpr int TILE = 1024;                          // rows per scatter tile
+constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
+constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
+constexpr int CCAP = 512;                           // candidate samples a warp evaluates per cooperative batch
+constexpr int FAST_CAP = 24;                        // occluders per beam held by the fast kernel (mean 1-5)
+constexpr int SLOW_CAP = 128;                       // ... by the overflow kernel
+constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel can take per call
+// kernel modes
+constexpr int MODE_SCAN = 0;      // every beam of the batch: candidate scan; beams without occluders are finished here,
+                                  // the others are pushed to the solve list
+constexpr int LIST_HDR_BYTES = 2048;  // ints: [0] solve count, [1] overflow count, [C..2C) class counts, [2C..3C) cursors
+constexpr int LIST_CLASSES = 128;  // solve list is counting-sorted by work class (target range) before the solve kernel
+constexpr int MODE_LIST = 1;      // one listed beam per thread (dense: every lane has occluders): scan again, claim,
+                                  // waveform, finish
+
+
+__device__ __forceinline__ void raise_status(int *status, int code) { atomicMax(status, code); }
+
+__device__ __forceinline__ int channel_bin(float ch)
+{
+    int c = (int)ch;
+    return (ch >= 0.0f && ch < 64.0f && (float)c == ch) ? c : LSS_N_CHANNELS;
+}
+
+__device__ __forceinline__ bool within(double diff, double tol)
+{
+    return (fabs(diff) < tol) || (fabs(diff - LSS_TWO_PI) < tol) || (fabs(diff + LSS_TWO_PI) < tol);
+}
+
+__device__ __forceinline__ double xsi64(double r)
+{
+    // simulation.py:553-569
+    if (r <= 0.9) return 0.0;
+    if (r >= 1.0) return 1.0;
+    const double m = (1 - 0) / (1.0 - 0.9);
+    const double b = 0 - (m * 0.9);
+    return __dadd_rn(__dmul_rn(m, r), b);
+}
+
+__device__ __forceinline__ double xsi32(float r)
+{
+    // same with a float32 argument: NumPy 2 keeps the comparison and m*R+b in float32
+    if (r <= 0.9f) return 0.0;
+    if (r >= 1.0f) return 1.0;
+    const double m = (1 - 0) / (1.0 - 0.9);
+    const double b = 0 - (m * 0.9);
+    return (double)__fadd_rn(__fmul_rn((float)m, r), (float)b);
+}
+
+
+// correctly rounded float32 of the float64 atan2 (simulation.py:91 uses a host-dependent float32 np.arctan2); out of
+// line: cold next to the injected-theta path and bulky
+__device__ __noinline__ float azimuth32(float y, float x)
+{
+    return (float)atan2((double)y, (double)x);
+}
+
+}  // namespace
+
+// solve.cu: the dense solve kernel over the (sorted) solve list; beams it cannot take (more than SOLVE_LCAP occluders or
+// a bucket prefix longer than it tracks) go to list_out for the overflow kernel.  hdr[2] is its tile cursor (zeroed).
+void lss_launch_solve(const DevArgs &a, int *tile_cursor, int n_sm, cudaStream_t stream);

@@ -67,6 +67,9 @@ struct lss_engine {
     SensorConst *d_sensor = nullptr;
     CameraConst *d_camera = nullptr;
     double *d_R = nullptr;              // range grid, LSS_M_EXT doubles
+    double2 *d_wtab = nullptr;          // (sin, cos)(pi R[k] / (c tau)), LSS_M_EXT entries (solve.cu)
+    int n_sm = 148;                     // multiprocessors of the device (persistent grids)
+    bool old_solve = false;             // LSS_OLD_SOLVE=1: round-1 solve kernel (A/B measurements)
     int *d_status = nullptr;            // latched asynchronous device status
     std::map<int, TableSet> tables;
     int next_table_id = 1;
@@ -177,7 +180,7 @@ inline cudaError_t lss_zero_async(lss_engine *e, const ZeroRegions &r, cudaStrea
 }
 
 enum { LSS_K_SORT = 0, LSS_K_PREPASS = 1, LSS_K_SNOWFALL = 2, LSS_K_COMPACT = 3, LSS_K_FINALIZE = 4, LSS_K_WET = 5,
-       LSS_K_FOG = 6, LSS_K_COUNT = 7 };
+       LSS_K_FOG = 6, LSS_K_SCAN = 7, LSS_K_SOLVE = 8, LSS_K_COUNT = 9 };   // 7, 8: inside the LSS_K_SNOWFALL bracket
 
 struct KernelTimer {        // RAII: records begin/end events when profiling is on
     lss_engine *e; cudaStream_t s; int idx = -1;
@@ -230,6 +233,8 @@ struct SnowfallArgs {
     const float *d_theta;
     const double *h_thresh_poly;
     const double *d_thresh_poly = nullptr;      // device-resident polynomials (host pipeline: pre-pass on another stream)
+    const double *h_plane_in = nullptr;         // device pre-pass: injected plane / bin picks (PrepassIO)
+    const int32_t *h_ymins_in = nullptr;
     double noise_floor;
     uint32_t flags;
     float *d_out_points;
@@ -262,9 +267,20 @@ __device__ __forceinline__ double lss_plane_dot(double x, double y, double z, co
     return __dadd_rn(__dadd_rn(__dmul_rn(x, w[0]), __dmul_rn(y, w[1])), __dmul_rn(z, w[2]));
 }
 int64_t lss_prepass_ws_bytes(int64_t n_total, int n_clouds);
+// Optional inputs / outputs of the pre-pass.  The two host inputs replay what the reference host drew / picked
+// (sklearn RANSAC plane, np.argpartition's pick among the least populated bins) so that everything downstream can be
+// compared with reference-generated fixtures; NULL = the device's own deterministic choice.
+struct PrepassIO {
+    const double *h_plane_in = nullptr;     // host [B*4] (w0, w1, w2, h)
+    const int32_t *h_ymins_in = nullptr;    // host [B*50] intensity-bin index per range bin (augmentation.py:236)
+    double *d_poly_out = nullptr;           // device [B*3]
+    double *d_plane_out = nullptr;          // device [B*4]
+    double *d_fit_out = nullptr;            // device [B*8]: lin slope, lin intercept, pmin slope, pmin intercept, ymax,
+                                            //               n_ground, n_window, flat-earth fallback taken
+    int32_t *d_ymins_out = nullptr;         // device [B*50] the picks used (-1: fewer than 3 ground points)
+};
 lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int32_t *d_cloud_cnt,
                            const int64_t *h_cloud_off, int n_clouds, double delta, double noise_floor, int flat_earth,
-                           int range64, int raise_few_ground, const double *h_plane_in,
-                           double *d_poly_out, double *d_plane_out, void *d_ws, int64_t ws_bytes, void **cloudpre_out,
-                           cudaStream_t stream);
+                           int range64, int raise_few_ground, const PrepassIO &io, void *d_ws, int64_t ws_bytes,
+                           void **cloudpre_out, cudaStream_t stream);
 int64_t lss_snowfall_ws_bytes(int64_t n_total, int n_clouds);

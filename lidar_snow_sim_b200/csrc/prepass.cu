@@ -47,6 +47,8 @@ struct PreArgs {
     double *partial;         // [B * max_blocks * 16]
     int max_blocks;
     int *status;
+    const int32_t *ymins_in; // optional [B*50]: injected picks of np.argpartition(hist, 2, axis=1)[:, 0] (augmentation.py:236)
+    int32_t *ymins;          // [B*50] the picks used (injected or the device's first-minimum rule)
 };
 
 __device__ __forceinline__ float range32(float x, float y, float z)
@@ -527,8 +529,14 @@ __global__ void __launch_bounds__(1024) k_hist_minima(PreArgs a)
             const int oi = __shfl_down_sync(0xffffffffu, bidx, s);
             if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
         }
+        if (a.ymins_in) {                       // parity replay: the reference host's own pick for this range bin
+            const int inj = a.ymins_in[b * HIST_NX + warp];
+            bidx = inj < 0 ? 0 : (inj >= HIST_NY ? HIST_NY - 1 : inj);
+        }
         if (lane == 0) {
-            const double mv = (bidx == HIST_NY) ? cp.ymax : (bidx * ystep + 5.0);      // yedges[ymins]
+            a.ymins[b * HIST_NX + warp] = bidx;
+            // yedges[ymins] with yedges = np.linspace(5, ymax, 2556): arange * step + start, last edge = stop
+            const double mv = (bidx == HIST_NY) ? cp.ymax : __dadd_rn(__dmul_rn((double)bidx, ystep), 5.0);
             okf[warp] = mv > 5.0;                                                       // augmentation.py:238
             ys[warp] = mv;
             const double e0 = warp * (60.0 / HIST_NX) + 10.0;
@@ -581,7 +589,8 @@ __global__ void __launch_bounds__(PP_TPB) k_poly_sums(PreArgs a)
     }
 }
 
-__global__ void k_poly_solve(PreArgs a, int n_blocks, double *poly_out /* [B*3] or null */, double *plane_out /* [B*4] or null */)
+__global__ void k_poly_solve(PreArgs a, int n_blocks, double *poly_out /* [B*3] or null */, double *plane_out /* [B*4] or null */,
+                             double *fit_out /* [B*8] or null */, int32_t *ymins_out /* [B*50] or null */)
 {
     const int b = blockIdx.x;
     CloudPre &cp = a.cp[b];
@@ -613,13 +622,19 @@ __global__ void k_poly_solve(PreArgs a, int n_blocks, double *poly_out /* [B*3] 
     cp.poly[2] = c0 - c1 * m / sc + c2 * m * m / (sc * sc);
     if (poly_out) { poly_out[3 * b] = cp.poly[0]; poly_out[3 * b + 1] = cp.poly[1]; poly_out[3 * b + 2] = cp.poly[2]; }
     if (plane_out) { plane_out[4 * b] = cp.w[0]; plane_out[4 * b + 1] = cp.w[1]; plane_out[4 * b + 2] = cp.w[2]; plane_out[4 * b + 3] = cp.h; }
+    if (fit_out) {
+        double *f = fit_out + 8 * b;
+        f[0] = cp.lin[0]; f[1] = cp.lin[1]; f[2] = cp.pmin[0]; f[3] = cp.pmin[1]; f[4] = cp.ymax;
+        f[5] = (double)cp.n_ground; f[6] = (double)cp.n_window; f[7] = (double)cp.flat;
+    }
+    if (ymins_out) for (int k = 0; k < HIST_NX; k++) ymins_out[b * HIST_NX + k] = cp.n_ground >= 3 ? a.ymins[b * HIST_NX + k] : -1;
 }
 
 inline int64_t align_up(int64_t v, int64_t al) { return (v + al - 1) / al * al; }
 
 }  // namespace
 
-struct PrepassLayout { int64_t cp, win, stage, tile_cnt, tile_base, hist, trial, partial, plane_in, total; int max_blocks; };
+struct PrepassLayout { int64_t cp, win, stage, tile_cnt, tile_base, hist, trial, partial, plane_in, ymins, ymins_in, total; int max_blocks; };
 
 static PrepassLayout prepass_layout(int64_t n_total, int n_clouds)
 {
@@ -635,6 +650,8 @@ static PrepassLayout prepass_layout(int64_t n_total, int n_clouds)
     L.trial = o;    o = align_up(o + (int64_t)n_clouds * RANSAC_T * 8 * 8, 256);
     L.partial = o;  o = align_up(o + (int64_t)n_clouds * L.max_blocks * 16 * 8, 256);
     L.plane_in = o; o = align_up(o + (int64_t)n_clouds * 4 * 8, 256);
+    L.ymins = o;    o = align_up(o + (int64_t)n_clouds * HIST_NX * 4, 256);
+    L.ymins_in = o; o = align_up(o + (int64_t)n_clouds * HIST_NX * 4, 256);
     L.total = o;
     return L;
 }
@@ -646,10 +663,11 @@ int64_t lss_prepass_ws_bytes(int64_t n_total, int n_clouds) { return prepass_lay
 // d_cloudpre_out: optional device pointer receiving the address of the per-cloud CloudPre records (for wet ground).
 lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_cloud_off, const int32_t *d_cloud_cnt,
                            const int64_t *h_cloud_off, int n_clouds, double delta, double noise_floor, int flat_earth,
-                           int range64, int raise_few_ground, const double *h_plane_in,
-                           double *d_poly_out, double *d_plane_out, void *d_ws, int64_t ws_bytes, void **cloudpre_out,
-                           cudaStream_t stream)
+                           int range64, int raise_few_ground, const PrepassIO &io, void *d_ws, int64_t ws_bytes,
+                           void **cloudpre_out, cudaStream_t stream)
 {
+    const double *h_plane_in = io.h_plane_in;
+    double *d_poly_out = io.d_poly_out, *d_plane_out = io.d_plane_out;
     const int B = n_clouds;
     const int64_t N = h_cloud_off[B];
     const PrepassLayout L = prepass_layout(N, B);
@@ -676,6 +694,12 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
     a.partial = (double *)(ws + L.partial);
     a.max_blocks = L.max_blocks;
     a.status = e->d_status;
+    a.ymins = (int32_t *)(ws + L.ymins);
+    a.ymins_in = nullptr;
+    if (io.h_ymins_in) {
+        LSS_CUDA_CHECK(e, lss_stage_upload(e, ws + L.ymins_in, io.h_ymins_in, sizeof(int32_t) * HIST_NX * B, stream));
+        a.ymins_in = (const int32_t *)(ws + L.ymins_in);
+    }
     if (cloudpre_out) *cloudpre_out = a.cp;
     int64_t max_n = 0;
     for (int b = 0; b < B; b++) max_n = std::max<int64_t>(max_n, h_cloud_off[b + 1] - h_cloud_off[b]);
@@ -715,7 +739,7 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
         k_ground_hist<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
         k_hist_minima<<<B, 1024, 0, stream>>>(a);
         k_poly_sums<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
-        k_poly_solve<<<B, 32, 0, stream>>>(a, nblk, d_poly_out, d_plane_out);
+        k_poly_solve<<<B, 32, 0, stream>>>(a, nblk, d_poly_out, d_plane_out, io.d_fit_out, io.d_ymins_out);
         e->launches += 5;
     }
     LSS_CUDA_CHECK(e, cudaGetLastError());

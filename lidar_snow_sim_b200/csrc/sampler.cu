@@ -80,6 +80,12 @@ extern "C" {
 //   pcg_state:    in/out, 4 x uint64 = PCG64 {state_hi, state_lo, inc_hi, inc_lo} of a numpy Generator
 //   h_xyr:        out, capacity rows of (x, y, r) float64
 // Returns LSS_ERR_WORKSPACE (and the required row count in *n_out is NOT known) if capacity is exceeded.
+// The reference squares SCALARS with `** 2` (python float.__pow__ / numpy's scalar power), i.e. through libm's pow(),
+// which is within 0.52 ulp but not always the correctly rounded x*x; GCC would fold pow(x, 2.0) into x*x, so the call
+// goes through a volatile pointer.  (Array expressions like (sx - x) ** 2 use np.square = x*x, sampling.py:170.)
+static double (*volatile libm_pow)(double, double) = pow;
+static inline double sq(double v) { return libm_pow(v, 2.0); }
+
 lss_status lss_dart_throwing(double occupancy_ratio, double precipitation_rate, double R_0, int distribution,
                              uint64_t *pcg_state, double *h_xyr, int64_t capacity, int64_t *n_out)
 {
@@ -99,8 +105,8 @@ lss_status lss_dart_throwing(double occupancy_ratio, double precipitation_rate, 
     grid.next.reserve(1 << 16);
     int64_t n = 0;
     double area_occupied = 0.0;
-    const double area_occupied_global = occupancy_ratio * PI * (R_0 * R_0);     // sampling.py:124
-    const double R0sq = R_0 * R_0;
+    const double area_occupied_global = occupancy_ratio * PI * sq(R_0);          // sampling.py:124
+    const double R0sq = sq(R_0);
     lss_status st = LSS_OK;
     while (area_occupied < area_occupied_global) {
         const double length = sqrt(g.uniform(0, R0sq));                          // :145
@@ -112,8 +118,8 @@ lss_status lss_dart_throwing(double occupancy_ratio, double precipitation_rate, 
         dia = dia / 1000;                                                        // :157
         const double height = g.uniform(-dia / 2, dia / 2);                      // :160
         const double half = dia / 2;
-        const double disk_radius = sqrt(half * half - height * height);         // :163
-        if (x * x + y * y <= disk_radius * disk_radius) continue;                // :166
+        const double disk_radius = sqrt(sq(half) - sq(height));                 // :163
+        if (sq(x) + sq(y) <= sq(disk_radius)) continue;                          // :166
         const int cx = grid.coord(x), cy = grid.coord(y);
         bool overlap = false;
         for (int gy = cy - 1; gy <= cy + 1 && !overlap; gy++) {
@@ -134,7 +140,7 @@ lss_status lss_dart_throwing(double occupancy_ratio, double precipitation_rate, 
         grid.next.push_back(grid.head[(size_t)cy * grid.n + cx]);
         grid.head[(size_t)cy * grid.n + cx] = (int32_t)n;
         n++;
-        area_occupied += PI * (disk_radius * disk_radius);                       // :181-182
+        area_occupied += PI * sq(disk_radius);                                   // :181-182
     }
     pcg_state[0] = (uint64_t)(g.state >> 64);
     pcg_state[1] = (uint64_t)g.state;

@@ -24,111 +24,13 @@
 // Numerics: everything the reference computes in float32 under NumPy 2 (range d, azimuth theta, the hard target's
 // waveform window and r^2) is computed in float32 with round-to-nearest, non-fused intrinsics so it is bit-identical;
 // the geometric narrow phase, the occlusion ratios and the waveform run in float64.
-#include "common.cuh"
+#include "beam.cuh"
 
 namespace {
-
-constexpr int SNOW_TPB = 128;
-constexpr int SNOW_WARPS = SNOW_TPB / 32;
-constexpr int TILE = 1024;                          // rows per scatter tile
-constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
-constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
-constexpr int CCAP = 512;                           // candidate samples a warp evaluates per cooperative batch
-constexpr int FAST_CAP = 24;                        // occluders per beam held by the fast kernel (mean 1-5)
-constexpr int SLOW_CAP = 128;                       // ... by the overflow kernel
-constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel can take per call
-// kernel modes
-constexpr int MODE_SCAN = 0;      // every beam of the batch: candidate scan; beams without occluders are finished here,
-                                  // the others are pushed to the solve list
-constexpr int LIST_HDR_BYTES = 2048;  // ints: [0] solve count, [1] overflow count, [C..2C) class counts, [2C..3C) cursors
-constexpr int LIST_CLASSES = 128;  // solve list is counting-sorted by work class (target range) before the solve kernel
-constexpr int MODE_LIST = 1;      // one listed beam per thread (dense: every lane has occluders): scan again, claim,
-                                  // waveform, finish
-
-struct DevArgs {
-    // tables
-    const ParticleRec *rec;
-    const BroadEntry *entries;
-    const int32_t *bucket_start;
-    int n_buckets;
-    int n_planes;
-    double inv_w, w;
-    // per call
-    const float *pts;            // rows in input order
-    const float *theta;          // optional, input order
-    const int64_t *cloud_off;    // [B+1] device
-    const int32_t *order;        // [B*64] device
-    const double *thresh;        // [B*3] device or null
-    const SensorConst *sensor;
-    const CameraConst *camera;
-    const double *R;
-    double half_div;             // radians(beam_divergence / 2)
-    double div_rad;              // radians(beam_divergence)
-    uint32_t flags;
-    float *aug;                  // [N*5] augmented rows, input order
-    uint8_t *code_keep;          // [N] channel bin of a kept row, 255 = dropped
-    uint8_t *code_all;           // optional [N] channel bin of every row (un-filtered debug output)
-    int32_t *nocc;               // optional [N], input order
-    unsigned *hist_keep;         // [sum of tiles * NBINS]; cloud b owns rows tile_base[b] .. tile_base[b+1]
-    unsigned *hist_all;          // optional
-    const int32_t *tile_base;    // [B+1] device
-    double *stats;               // [B*4]: num_attenuated, num_removed, avg_diff, diff_sum
-    int *counters;               // [B*2]: num_attenuated (threshold-kept), num_removed
-    unsigned *att_cnt;           // [B*64] label-1 beams per channel (all of them, simulation.py:170)
-    unsigned long long *att_sum; // [B] sum of their new integer intensities
-    int *status;
-    // work lists (cloud << 32 | row): the scan kernel defers every beam that has occluders to the dense solve kernel,
-    // which in turn defers beams with more than FAST_CAP occluders to the overflow kernel
-    const unsigned long long *list_in;
-    const int *count_in;
-    int cap_in;
-    unsigned long long *list_out;
-    int *count_out;
-    int cap_out;
-};
-
-__device__ __forceinline__ void raise_status(int *status, int code) { atomicMax(status, code); }
-
-__device__ __forceinline__ int channel_bin(float ch)
-{
-    int c = (int)ch;
-    return (ch >= 0.0f && ch < 64.0f && (float)c == ch) ? c : LSS_N_CHANNELS;
-}
-
-__device__ __forceinline__ bool within(double diff, double tol)
-{
-    return (fabs(diff) < tol) || (fabs(diff - LSS_TWO_PI) < tol) || (fabs(diff + LSS_TWO_PI) < tol);
-}
-
-__device__ __forceinline__ double xsi64(double r)
-{
-    // simulation.py:553-569
-    if (r <= 0.9) return 0.0;
-    if (r >= 1.0) return 1.0;
-    const double m = (1 - 0) / (1.0 - 0.9);
-    const double b = 0 - (m * 0.9);
-    return __dadd_rn(__dmul_rn(m, r), b);
-}
-
-__device__ __forceinline__ double xsi32(float r)
-{
-    // same with a float32 argument: NumPy 2 keeps the comparison and m*R+b in float32
-    if (r <= 0.9f) return 0.0;
-    if (r >= 1.0f) return 1.0;
-    const double m = (1 - 0) / (1.0 - 0.9);
-    const double b = 0 - (m * 0.9);
-    return (double)__fadd_rn(__fmul_rn((float)m, r), (float)b);
-}
 
 // Cold or bulky pieces are kept out of line and data-dependent loops are not unrolled: the beam kernel is
 // instruction-fetch sensitive (profiles/: `no_inst` stalls grow with its SASS size), every instruction that is not
 // on the common path costs fetch bandwidth for all resident warps.
-__device__ __noinline__ float azimuth32(float y, float x)
-{
-    // correctly rounded float32 of the float64 atan2 (simulation.py:91 uses a host-dependent float32 np.arctan2)
-    return (float)atan2((double)y, (double)x);
-}
-
 // one waveform sample: sum over the pulses q0..q1 whose window contains k, in dict order (simulation.py:148-149)
 __device__ __noinline__ double waveform_sample(int k, double Rk, int q0, int q1, const double *amp, const double *r,
                                                const int *ks, const int *ke)
@@ -939,8 +841,12 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         LSS_CUDA_CHECK(e, lss_side_stream(e, &side, &ev_fork, &ev_join));
         LSS_CUDA_CHECK(e, cudaEventRecord(ev_fork, stream));            // after the offsets upload above
         LSS_CUDA_CHECK(e, cudaStreamWaitEvent(side, ev_fork, 0));
+        PrepassIO io;
+        io.h_plane_in = s.h_plane_in;
+        io.h_ymins_in = s.h_ymins_in;
+        io.d_poly_out = d_thresh;
         lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
-                                        nullptr, d_thresh, nullptr, ws + w.prepass, w.prepass_bytes, nullptr, side);
+                                        io, ws + w.prepass, w.prepass_bytes, nullptr, side);
         const cudaError_t je = cudaEventRecord(ev_join, side);
         if (ps != LSS_OK || je != cudaSuccess) {
             cudaStreamWaitEvent(stream, ev_join, 0);                    // never leave the side stream dangling
@@ -964,6 +870,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.sensor = e->d_sensor;
     a.camera = e->d_camera;
     a.R = e->d_R;
+    a.wtab = e->d_wtab;
     a.half_div = (s.beam_divergence_deg / 2) * (LSS_PI / 180.0);
     a.div_rad = div_rad;
     a.flags = s.flags;
@@ -988,17 +895,26 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         a.list_in = nullptr; a.count_in = nullptr; a.cap_in = 0;
         a.list_out = d_solve_list; a.count_out = d_counts2; a.cap_out = (int)std::min<int64_t>(N, 0x7fffffff);
         dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
-        k_snowfall<FAST_CAP, MODE_SCAN><<<grid, SNOW_TPB, 0, stream>>>(a);
+        {
+            KernelTimer ks(e, LSS_K_SCAN, stream);
+            k_snowfall<FAST_CAP, MODE_SCAN><<<grid, SNOW_TPB, 0, stream>>>(a);
+        }
         // 2. solve: the listed beams, densely packed (every lane has occluders); CTAs beyond the list exit at once
         k_list_sort<<<(unsigned)((N + 256 * SORT_PER_THREAD - 1) / (256 * SORT_PER_THREAD)), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, a.cap_out);
         a.list_in = d_sorted_list; a.count_in = d_counts2; a.cap_in = a.cap_out;
         a.list_out = d_ovf_list; a.count_out = d_counts2 + 1; a.cap_out = OVF_LIST_CAP;
-        k_snowfall<FAST_CAP, MODE_LIST><<<(unsigned)((N + SNOW_TPB - 1) / SNOW_TPB), SNOW_TPB, 0, stream>>>(a);
+        {
+            KernelTimer ks(e, LSS_K_SOLVE, stream);
+            if (e->old_solve)        // round-1 list kernel (A/B measurements: LSS_OLD_SOLVE=1)
+                k_snowfall<FAST_CAP, MODE_LIST><<<(unsigned)((N + SNOW_TPB - 1) / SNOW_TPB), SNOW_TPB, 0, stream>>>(a);
+            else
+                lss_launch_solve(a, d_counts2 + 2, e->n_sm, stream);
+        }
         // 3. overflow: beams with more than FAST_CAP occluders (rare), redone with SLOW_CAP
         a.list_in = d_ovf_list; a.count_in = d_counts2 + 1; a.cap_in = OVF_LIST_CAP;
         a.list_out = nullptr; a.count_out = nullptr; a.cap_out = 0;
         k_snowfall<SLOW_CAP, MODE_LIST><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
-        e->launches += 3;
+        e->launches += 1;           // (+ one each from the three KernelTimer brackets = 4 launches)
     }
     if (ev_join) LSS_CUDA_CHECK(e, cudaStreamWaitEvent(stream, ev_join, 0));
     {

@@ -1,0 +1,444 @@
+// solve.cu -- the dense solve kernel: every beam of the (work-class sorted) solve list has at least one occluder.
+//
+// Replaces, per listed beam, get_occlusions + compute_occlusion_dict + the waveform loop of process_single_channel
+// (tools/snowfall/simulation.py:118-188, 231-424).  Design (round 2; the round-1 kernel kept per-thread lists in local
+// memory -- 180 MB of it across the resident threads, thrashing L2 -- published one descriptor per waveform sample
+// lane-serially and evaluated a float64 sinpi per sample and pulse):
+//
+//   * persistent grid, one warp = one tile of 32 listed beams, tiles handed out by an atomic cursor (the list is sorted
+//     costliest class first, so the tail is cheap tiles);
+//   * NO local memory: the beams of a warp share a shared-memory arena of ARENA slots, allocated exactly
+//     (occluders + 1 per beam) with a warp scan after a counting pass over the beam's bucket prefix; the counting pass
+//     leaves a 64-bit hit mask, so the fill pass only touches the hits again;
+//   * nearest-first claiming runs in place in the arena: the union list lives in the slots of the already processed
+//     hits, pulses (range, ratio) are compacted to the front;
+//   * waveform: sin(pi (R_k - r) / (c tau)) = sin(pi a_k) cos(pi b) - cos(pi a_k) sin(pi b) with a_k = R_k / (c tau) from a
+//     1230-entry table (host, extended precision) and b = r / (c tau) evaluated once per pulse (one sincospi), so a
+//     sample costs a 16-byte load and six float64 operations instead of a sinpi;
+//   * an isolated pulse is unimodal: its owner evaluates the three samples around the peak itself; groups of
+//     overlapping pulses are summed over their whole union window (in dict order, like the reference's i[k] +=) by ALL 32
+//     lanes of the warp, one group at a time, and reduced with three integer warp reductions (first maximum wins,
+//     np.argmax).
+//
+// Beams the arena cannot take (more than SOLVE_LCAP occluders) go to the overflow list and are redone by the
+// round-1 list kernel (snowfall.cu, k_snowfall<SLOW_CAP, MODE_LIST>), which has no such limit below 128.
+#include "beam.cuh"
+
+namespace {
+
+constexpr int SOLVE_TPB = 128;
+constexpr int SOLVE_WARPS = SOLVE_TPB / 32;
+constexpr int SOLVE_CTAS_PER_SM = 6;
+constexpr int ARENA = 256;                 // slots per warp: sum over the 32 beams of (occluders + 1); more -> extra round
+constexpr int SOLVE_LCAP = 63;             // occluders per beam handled here (needs LCAP + 1 <= ARENA)
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Beam {                              // what the narrow phase needs of a beam
+    double d, right, left;
+    bool straddle;
+};
+
+// simulation.py:345-385 for one particle: planar range strictly below the target range, centre inside the beam or
+// disk crossing one of the two limit rays
+__device__ __forceinline__ bool exact_hit(const ParticleRec *rp, const Beam &bm, double &rho, bool &right_hit, bool &left_hit)
+{
+    rho = rp->rho;
+    if (!(rho < bm.d)) return false;
+    const double phi = rp->phi, alpha = rp->alpha;
+    bool inside = (bm.right <= phi) && (phi <= bm.left);
+    if (bm.straddle) inside = inside || ((bm.right - LSS_TWO_PI <= phi) && (phi <= bm.left)) ||
+                              ((bm.right <= phi) && (phi <= bm.left + LSS_TWO_PI));
+    right_hit = within(bm.right - phi, alpha);
+    left_hit = within(bm.left - phi, alpha);
+    return inside || right_hit || left_hit;
+}
+
+__device__ __forceinline__ unsigned long long pack_win(int ks, int ke, int k0)
+{
+    return (unsigned long long)(unsigned)ks | ((unsigned long long)(unsigned)ke << 11) | ((unsigned long long)(unsigned)k0 << 22);
+}
+
+// sin / cos of pi * r / (c tau) to ~1 ulp of the ANGLE: quotient in two pieces (the float64 quotient alone is off by up
+// to 4e-15 in an argument of ~40), sincospi of the leading piece, first-order correction for the rest
+__device__ __forceinline__ void pulse_phase(double r, double &sb, double &cb)
+{
+    const double ctau = 299792458.0 * 1e-8, inv_ctau = 1.0 / (299792458.0 * 1e-8);
+    const double bh = r * inv_ctau;
+    const double bl = fma(-bh, ctau, r) * inv_ctau;
+    double s, c;
+    sincospi(bh, &s, &c);
+    const double corr = LSS_PI * bl;
+    sb = fma(corr, c, s);
+    cb = fma(-corr, s, c);
+}
+
+__global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs a, int *tile_cursor)
+{
+    __shared__ double s_arena[SOLVE_WARPS][4][ARENA];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // slot arrays of this warp.  Phase 1 (hits): A0 = a1, A1 = a2, A2 = planar range.  Claiming: A0 / A1 prefix = union
+    // list, A2 / A3 prefix = (range, ratio) of the claiming particles.  Phase 2 (pulses): A0 = amplitude, A1 = sin phase,
+    // A3 = cos phase, A2 = packed (first sample, end sample, sample nearest to the peak).
+    double *A0 = s_arena[wid][0], *A1 = s_arena[wid][1], *A2 = s_arena[wid][2], *A3 = s_arena[wid][3];
+    unsigned long long *W = reinterpret_cast<unsigned long long *>(A2);
+
+    const int cnt = min(*a.count_in, a.cap_in);
+    const int n_tiles = (cnt + 31) >> 5;
+    const double ctau = 299792458.0 * 1e-8;
+    const double inv_step = (double)(LSS_M_EXT - 1) / (120 + ctau);
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_cursor, 1);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= n_tiles) break;
+        const int slot = tile * 32 + lane;
+        const bool active = slot < cnt;
+        const unsigned long long it = active ? a.list_in[slot] : 0ull;
+        const int b = (int)((it >> 32) & 0xffffu);
+        const int i = (int)(it & 0xffffffffu);
+        const int64_t beg = a.cloud_off[b];
+        float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
+        if (active) {
+            const float *row = a.pts + (beg + i) * 5;
+            px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
+        }
+        // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
+        const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+        const int ch = channel_bin(pch);
+        const bool valid = active && ch < LSS_N_CHANNELS;
+
+        float out_x = px, out_y = py, out_z = pz, out_i = pint, out_l = valid ? 0.0f : pch;
+        long long att_new_i = -1;
+        int n_claim = 0;
+
+        // ---- beam limits (simulation.py:91-101) and the counting pass over the beam's azimuth bucket -------------------
+        Beam bm;
+        bm.d = (double)d32;
+        bm.right = bm.left = 0.0;
+        bm.straddle = false;
+        int e0 = 0, plen = 0, L = 0;
+        unsigned long long mask = 0ull;
+        float th_rel = 0.0f;
+        if (valid) {
+            float th32 = a.theta ? a.theta[beg + i] : azimuth32(py, px);
+            if (th32 < 0.0f) th32 = __fadd_rn(th32, 6.2831855f);
+            const double thd = (double)th32;
+            double right = thd - a.half_div, left = thd + a.half_div;
+            if (right < 0) right += LSS_TWO_PI;
+            if (left < 0) left += LSS_TWO_PI;
+            if (right > LSS_TWO_PI) right -= LSS_TWO_PI;
+            if (left > LSS_TWO_PI) left -= LSS_TWO_PI;
+            bm.right = right; bm.left = left; bm.straddle = right > left;
+            const int plane = a.order[b * LSS_N_CHANNELS + ch];
+            if (plane >= 0 && plane < a.n_planes && thd == thd) {
+                const double thm = thd >= LSS_TWO_PI ? thd - LSS_TWO_PI : thd;
+                int bk = (int)(thm * a.inv_w);
+                bk = bk < 0 ? 0 : (bk >= a.n_buckets ? a.n_buckets - 1 : bk);
+                th_rel = (float)(thm - (bk + 0.5) * a.w);
+                const int32_t *bs = a.bucket_start + (int64_t)plane * (a.n_buckets + 1) + bk;
+                e0 = bs[0];
+                const int e1 = bs[1];
+                int e = e0;
+#pragma unroll 1
+                for (; e < e1; e++) {
+                    const BroadEntry en = __ldg(&a.entries[e]);
+                    if (!(en.x < d32)) break;                       // sorted by range: nothing nearer follows
+                    if (!(fabsf(en.y - th_rel) <= en.z)) continue;   // float32 broad phase (conservative)
+                    double rho;
+                    bool rh, lh;
+                    if (!exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) continue;
+                    const int t = e - e0;
+                    if (t < 64) mask |= 1ull << t;
+                    L++;
+                }
+                plen = e - e0;
+            }
+        }
+        const bool deferred = L > SOLVE_LCAP;
+        if (deferred) {
+            const int s2 = atomicAdd(a.count_out, 1);
+            if (s2 < a.cap_out) a.list_out[s2] = ((unsigned long long)b << 32) | (unsigned)i;
+            else raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
+        }
+        const int need = (valid && L > 0 && !deferred) ? L + 1 : 0;
+
+        // ---- rounds: as many beams of the tile as fit into the arena (normally all of them) ---------------------------
+        unsigned remaining = __ballot_sync(FULL, need > 0);
+        while (remaining) {
+            const bool rem = (remaining >> lane) & 1u;
+            const int mine = rem ? need : 0;
+            int incl = mine;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, s);
+                if (lane >= s) incl += t;
+            }
+            const bool in_round = rem && incl <= ARENA;
+            remaining &= ~__ballot_sync(FULL, in_round);
+            const int off = incl - mine;
+            int n_pulses = 0;
+            double best = 0.0;
+            int kbest = 0;
+
+            if (in_round) {
+                // ---- fill pass: (a1, a2, range) of every hit, inserted by range (np.argsort, simulation.py:416) -------
+                int nh = 0;
+                auto add_hit = [&](const ParticleRec *rp, double rho, bool right_hit, bool left_hit) {
+                    const double a1 = right_hit ? bm.right : rp->t_right;      // geometry.py:26-27
+                    const double a2 = left_hit ? bm.left : rp->t_left;
+                    int j = off + nh - 1;
+#pragma unroll 1
+                    while (j >= off && A2[j] > rho) { A0[j + 1] = A0[j]; A1[j + 1] = A1[j]; A2[j + 1] = A2[j]; j--; }
+                    A0[j + 1] = a1; A1[j + 1] = a2; A2[j + 1] = rho;
+                    nh++;
+                };
+                unsigned long long m = mask;
+#pragma unroll 1
+                while (m) {
+                    const int t = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const BroadEntry en = __ldg(&a.entries[e0 + t]);
+                    const ParticleRec *rp = a.rec + __float_as_int(en.w);
+                    double rho;
+                    bool rh, lh;
+                    exact_hit(rp, bm, rho, rh, lh);
+                    add_hit(rp, rho, rh, lh);
+                }
+#pragma unroll 1
+                for (int t = 64; t < plen; t++) {                   // long prefixes (dense tables, far targets)
+                    const BroadEntry en = __ldg(&a.entries[e0 + t]);
+                    if (!(fabsf(en.y - th_rel) <= en.z)) continue;
+                    const ParticleRec *rp = a.rec + __float_as_int(en.w);
+                    double rho;
+                    bool rh, lh;
+                    if (!exact_hit(rp, bm, rho, rh, lh)) continue;
+                    add_hit(rp, rho, rh, lh);
+                }
+
+                // ---- compute_occlusion_dict (simulation.py:231-295) ------------------------------------------------------
+                // Union-list formulation (see snowfall.cu): a particle claims |[a1,a2]| - |[a1,a2] n union of the claims so
+                // far| and is dropped iff its interval is contained in one union interval (or is empty); the hard target
+                // gets what is left between the smallest and the largest end point -- seam quirk included.
+                double rb = bm.right;
+                if (bm.straddle) rb = bm.right - LSS_TWO_PI;
+                int nu = 0, P = 0;
+                double ep_min = fmin(rb, bm.left), ep_max = fmax(rb, bm.left), claimed_total = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < L; j++) {
+                    double lo = A0[off + j];
+                    const double hi = A1[off + j], rho = A2[off + j];
+                    if (bm.straddle && lo > hi) lo -= LSS_TWO_PI;              // simulation.py:260-263
+                    ep_min = fmin(ep_min, fmin(lo, hi));
+                    ep_max = fmax(ep_max, fmax(lo, hi));
+                    if (!(lo < hi)) continue;
+                    bool contained = false;
+                    double cov = 0.0;
+#pragma unroll 1
+                    for (int u = 0; u < nu; u++) {
+                        const double ul = A0[off + u], uh = A1[off + u];
+                        contained |= (ul <= lo) && (hi <= uh);
+                        const double ov = fmin(hi, uh) - fmax(lo, ul);
+                        if (ov > 0.0) cov += ov;
+                    }
+                    if (contained) continue;
+                    const double claimed = (hi - lo) - cov;
+                    claimed_total += claimed;
+                    double nlo = lo, nhi = hi;      // merge [lo, hi] into the union (absorb overlapping / touching pieces)
+                    int w = 0;
+#pragma unroll 1
+                    for (int u = 0; u < nu; u++) {
+                        const double ul = A0[off + u], uh = A1[off + u];
+                        if (ul <= hi && uh >= lo) {
+                            nlo = fmin(nlo, ul);
+                            nhi = fmax(nhi, uh);
+                        } else {
+                            A0[off + w] = ul; A1[off + w] = uh; w++;
+                        }
+                    }
+                    A0[off + w] = nlo; A1[off + w] = nhi;       // w <= nu <= P <= j: only slots of processed hits
+                    nu = w + 1;
+                    double ratio = claimed / a.div_rad;
+                    ratio = ratio < 0 ? 0 : (ratio > 1 ? 1 : ratio);
+                    A2[off + P] = rho;
+                    A3[off + P] = ratio;
+                    P++;
+                }
+                n_claim = P;
+                double ratio_hard = ((ep_max - ep_min) - claimed_total) / a.div_rad;
+                ratio_hard = ratio_hard < 0 ? 0 : (ratio_hard > 1 ? 1 : ratio_hard);
+
+                if (P > 0) {
+                    // ---- pulses of the waveform (simulation.py:137-149) --------------------------------------------------
+                    const double beta_0 = 1 * 1e-06 / LSS_PI;
+                    const double i_orig = 0.9 * a.sensor->max_intensity[ch];
+                    const double A = (i_orig / beta_0) * beta_0;        // CA_P0 * beta_0 (quirk: every pulse uses it)
+                    bool bad = false;
+#pragma unroll 1
+                    for (int j = 0; j < P; j++) {
+                        const double r = A2[off + j], ratio = A3[off + j];
+                        const int ks = (int)ceil(r * 10);
+                        const int ke = (int)(floor((r + ctau) * 10) + 1);
+                        bad |= (ke > LSS_M_EXT) || (ks < 0);
+                        double sb, cb;
+                        pulse_phase(r, sb, cb);
+                        A0[off + j] = (A * ratio * xsi64(r)) / (r * r);
+                        A1[off + j] = sb;
+                        A3[off + j] = cb;
+                        W[off + j] = pack_win(ks, ke, (int)rint((r + ctau / 2) * inv_step));
+                    }
+                    {   // hard target: r_j is float32 => float32 index arithmetic and r^2
+                        const int ks = (int)ceilf(__fmul_rn(d32, 10.0f));
+                        const int ke = (int)(floorf(__fmul_rn(__fadd_rn(d32, (float)ctau), 10.0f)) + 1.0f);
+                        bad |= (ke > LSS_M_EXT) || (ks < 0);
+                        double sb, cb;
+                        pulse_phase(bm.d, sb, cb);
+                        A0[off + P] = (A * ratio_hard * xsi32(d32)) / (double)__fmul_rn(d32, d32);
+                        A1[off + P] = sb;
+                        A3[off + P] = cb;
+                        W[off + P] = pack_win(ks, ke, (int)rint((bm.d + ctau / 2) * inv_step));
+                    }
+                    if (bad) raise_status(a.status, LSS_ERR_RANGE_INDEX);
+                    else n_pulses = P + 1;
+                }
+            }
+
+            // ---- argmax of the summed waveform (simulation.py:148-153) -----------------------------------------------------
+            // Only samples inside some pulse window are non-zero.  Pulses whose windows overlap form a group whose samples
+            // are summed in full; an isolated pulse A sin^2(pi (R - r)/(c tau)) is unimodal and symmetric about
+            // r + c tau / 2, so its maximum over the grid is at one of the three samples around the sample nearest to the peak.
+            auto update = [&](double v, int k) {
+                if (v > best || (v == best && v > 0.0 && k < kbest)) { best = v; kbest = k; }
+            };
+            int j = 0;
+            bool have = false;
+            int g_klo = 0, g_khi = 0, g_q0 = 0, g_q1 = 0;
+            auto advance = [&]() {        // isolated pulses are solved on the way; stops at the next group
+                have = false;
+#pragma unroll 1
+                while (j < n_pulses) {
+                    const unsigned long long w0 = W[off + j];
+                    const int ks = (int)(w0 & 2047u), ke = (int)((w0 >> 11) & 2047u), k0 = (int)((w0 >> 22) & 2047u);
+                    int g1 = j, k_lo = ks, k_hi = ke;
+#pragma unroll 1
+                    while (g1 + 1 < n_pulses) {
+                        const unsigned long long w1 = W[off + g1 + 1];
+                        const int ks1 = (int)(w1 & 2047u);
+                        if (!(ks1 < k_hi)) break;
+                        g1++;
+                        k_lo = min(k_lo, ks1);
+                        k_hi = max(k_hi, (int)((w1 >> 11) & 2047u));
+                    }
+                    if (g1 > j) {
+                        g_klo = k_lo; g_khi = k_hi; g_q0 = off + j; g_q1 = off + g1;
+                        j = g1 + 1;
+                        have = true;
+                        return;
+                    }
+                    const double amp = A0[off + j], sb = A1[off + j], cb = A3[off + j];
+                    const int lo = max(ks, k0 - 1), hi = min(ke, k0 + 2);
+#pragma unroll 1
+                    for (int k = lo; k < hi; k++) {
+                        const double2 t = __ldg(&a.wtab[k]);
+                        const double sn = t.x * cb - t.y * sb;
+                        update(amp * (sn * sn), k);
+                    }
+                    j++;
+                }
+            };
+            if (n_pulses > 0) advance();
+            __syncwarp();
+            unsigned gm;
+            while ((gm = __ballot_sync(FULL, have)) != 0u) {
+#pragma unroll 1
+                for (unsigned mm = gm; mm; mm &= mm - 1) {
+                    const int src = __ffs(mm) - 1;
+                    const int klo = __shfl_sync(FULL, g_klo, src), khi = __shfl_sync(FULL, g_khi, src);
+                    const int q0 = __shfl_sync(FULL, g_q0, src), q1 = __shfl_sync(FULL, g_q1, src);
+                    double gb = 0.0;
+                    unsigned gk = 0u;
+#pragma unroll 1
+                    for (int base = klo; base < khi; base += 32) {
+                        const int k = base + lane;
+                        const bool on = k < khi;
+                        double v = 0.0;
+                        if (on) {
+                            const double2 t = __ldg(&a.wtab[k]);
+#pragma unroll 1
+                            for (int q = q0; q <= q1; q++) {
+                                const unsigned long long wq = W[q];
+                                if (k >= (int)(wq & 2047u) && k < (int)((wq >> 11) & 2047u)) {
+                                    const double sn = t.x * A3[q] - t.y * A1[q];
+                                    v += A0[q] * (sn * sn);          // pulses in dict order, like the reference's i[k] +=
+                                }
+                            }
+                        }
+                        // warp argmax (non-negative doubles order like their bit patterns): max high word, max low word
+                        // among those, min sample index among the exact ties -> the first maximum, like np.argmax
+                        const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+                        const unsigned vhi = (unsigned)(vb >> 32), vlo = (unsigned)vb;
+                        const unsigned mhi = __reduce_max_sync(FULL, vhi);
+                        const unsigned mlo = __reduce_max_sync(FULL, vhi == mhi ? vlo : 0u);
+                        const bool is_max = on && (vhi == mhi) && (vlo == mlo);
+                        const unsigned kmin = __reduce_min_sync(FULL, is_max ? (unsigned)k : 0xffffffffu);
+                        const double vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+                        if (vmax > gb) { gb = vmax; gk = kmin; }      // ascending windows: the earlier sample keeps a tie
+                    }
+                    if (lane == src && gb > 0.0) update(gb, (int)gk);
+                }
+                if (have) advance();
+                __syncwarp();
+            }
+
+            if (n_pulses > 0) {
+                // ---- new range / intensity / label (simulation.py:151-188) -------------------------------------------------
+                const double max_i = a.sensor->max_intensity[ch];
+                const double min_i = a.sensor->min_intensity[ch];
+                const double d_max = ((double)kbest / 10) - (ctau / 2);
+                const double q1 = 1 - d_max / 120;
+                double i_max = best + max_i * a.sensor->focal_slope[ch] * fabs(a.sensor->focal_offset[ch] - q1 * q1);
+                i_max = i_max < min_i ? min_i : (i_max > max_i ? max_i : i_max);
+                const long long new_i = (long long)i_max;       // int(): truncation
+                if (fabs(d_max - bm.d) < 2 * (1.0 / 10)) {
+                    out_l = 1.0f;
+                    att_new_i = new_i;                          // intensity_diff_sum += i_orig - new_i   (simulation.py:170)
+                } else {
+                    out_l = 2.0f;
+                    const double sc = d_max / bm.d;
+                    out_x = (float)((double)px * sc);
+                    out_y = (float)((double)py * sc);
+                    out_z = (float)((double)pz * sc);
+                }
+                if (new_i < 0) raise_status(a.status, LSS_ERR_NEGATIVE_INTENSITY);
+                double ci = (double)new_i;
+                ci = ci < min_i ? min_i : (ci > max_i ? max_i : ci);
+                out_i = (float)ci;
+            }
+            __syncwarp();
+        }
+
+        // ---- np.round of the intensity column (simulation.py:516), store, label-1 statistics (simulation.py:170) ----------
+        const bool counted = active && !deferred;          // a deferred beam is written by the overflow kernel
+        if (counted) {
+            float *row = a.aug + (beg + i) * 5;
+            row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = rintf(out_i); row[4] = out_l;
+            if (a.nocc) a.nocc[beg + i] = n_claim;
+        }
+        {
+            const bool on = counted && att_new_i >= 0;
+            const int key = b * LSS_N_CHANNELS + (ch < LSS_N_CHANNELS ? ch : 0);
+            const unsigned mk = __match_any_sync(FULL, on ? key : -1);
+            if (on && lane == __ffs(mk) - 1) atomicAdd(a.att_cnt + key, (unsigned)__popc(mk));
+            const unsigned mb = __match_any_sync(FULL, on ? b : -1);
+            const unsigned sum = __reduce_add_sync(mb, on ? (unsigned)att_new_i : 0u);
+            if (on && lane == __ffs(mb) - 1) atomicAdd(&a.att_sum[b], (unsigned long long)sum);
+        }
+    }
+}
+
+}  // namespace
+
+void lss_launch_solve(const DevArgs &a, int *tile_cursor, int n_sm, cudaStream_t stream)
+{
+    k_solve<<<(unsigned)(n_sm * SOLVE_CTAS_PER_SM), SOLVE_TPB, 0, stream>>>(a, tile_cursor);
+}

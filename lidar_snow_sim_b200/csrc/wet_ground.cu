@@ -235,9 +235,9 @@ int64_t lss_wet_ground_workspace_bytes(int64_t n_total, int n_clouds)
 lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int64_t *h_cloud_offsets,
                                 const int32_t *d_cloud_counts, int n_clouds, double water_height, double pavement_depth,
                                 double noise_floor, double power_factor, int flat_earth, double delta, int replace,
-                                const double *h_plane_in, float *d_out_points, double *d_out_intensity64,
-                                int32_t *d_out_counts, int32_t *d_out_passthrough, double *d_out_plane,
-                                void *d_workspace, int64_t workspace_bytes, void *stream)
+                                const double *h_plane_in, const int32_t *h_ymins_in, float *d_out_points,
+                                double *d_out_intensity64, int32_t *d_out_counts, int32_t *d_out_passthrough,
+                                double *d_out_plane, void *d_workspace, int64_t workspace_bytes, void *stream)
 {
     if (!e) return LSS_ERR_INVALID_ARG;
     if (!h_cloud_offsets || n_clouds < 0 || !d_out_points || !d_out_counts || !d_workspace)
@@ -269,8 +269,12 @@ lss_status lss_wet_ground_batch(lss_engine *e, const float *d_points, const int6
         }
         void *cp_ptr = nullptr;
         // the plane is fitted on the cloud as given; laser parameters over the |p.w+h| < delta band, float64 ranges
+        PrepassIO io;
+        io.h_plane_in = h_plane_in;
+        io.h_ymins_in = h_ymins_in;
+        io.d_plane_out = d_out_plane;
         rc = lss_prepass_run(e, d_points, d_off, d_cloud_counts, h_cloud_offsets, B, delta, noise_floor, flat_earth, 1, 0,
-                             h_plane_in, nullptr, d_out_plane, ws + L.prepass, L.prepass_bytes, &cp_ptr, st);
+                             io, ws + L.prepass, L.prepass_bytes, &cp_ptr, st);
         if (rc != LSS_OK) break;
         WetArgs a;
         a.pts = d_points;

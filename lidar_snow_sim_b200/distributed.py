@@ -129,3 +129,96 @@ class ShardedAugmenter:
         if not gather:
             return res, (lo, hi)
         return all_gather_augmented(res['points'], off, res['counts'], res['stats'], group=self.group), (lo, hi)
+
+
+class BatchGather:
+    """
+    The all-gather of BASELINE.json configs[3] for a stream of steps: every rank contributes its fixed-stride
+    augmented batch ((n_rows, 5) float32, slot-compacted) + per-cloud counts, double-buffered so that the exchange of
+    step k overlaps the kernels of step k + 1.
+
+    kind 'ce'   (default when torch's symmetric memory is usable): the gathered buffers are symmetric allocations; each
+                rank PUSHES its slot into every peer's buffer with peer-to-peer device copies on a side stream.  Large
+                device-to-device copies run on the copy engines over NVLink, so no SM is taken from the (latency-bound)
+                beam kernels -- the SM-resident channels of ncclAllGather slowed them by up to 20 % at 8 GPUs (round 1).
+    kind 'nccl' dist.all_gather_into_tensor(async_op=True) on NCCL's stream (also what the gloo CPU tests exercise).
+
+    Completion: `wait(j)` makes the caller's stream wait for THIS rank's outgoing copies of buffer j; a consumer that
+    reads a gathered buffer needs a barrier across ranks first (bench.py brackets end with one).  LSS_GATHER=nccl|ce
+    overrides the choice.
+    """
+
+    def __init__(self, n_rows, n_clouds, device, depth=2, group=None, kind=None):
+        import os
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_rows, self.n_clouds, self.depth = int(n_rows), int(n_clouds), depth
+        self.device = device
+        kind = kind or os.environ.get('LSS_GATHER') or ('ce' if getattr(device, 'type', 'cpu') == 'cuda' else 'nccl')
+        self.pending = [None] * depth
+        self.kind = 'nccl'
+        self.points = self.counts = None
+        if kind == 'ce':
+            try:
+                self._init_ce()
+                self.kind = 'ce'
+            except Exception as exc:                      # symmetric memory unavailable: fall back, say so
+                self.fallback_reason = f'{type(exc).__name__}: {exc}'
+        if self.kind == 'nccl':
+            self.points = [torch.empty((self.world * self.n_rows, 5), dtype=torch.float32, device=device)
+                           for _ in range(depth)]
+            self.counts = [torch.empty((self.world * self.n_clouds,), dtype=torch.int32, device=device)
+                           for _ in range(depth)]
+
+    def _init_ce(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.points, self.counts, self._peer_pts, self._peer_cnt = [], [], [], []
+        for _ in range(self.depth):
+            p = symm_mem.empty((self.world * self.n_rows, 5), dtype=torch.float32, device=self.device)
+            c = symm_mem.empty((self.world * self.n_clouds,), dtype=torch.int32, device=self.device)
+            hp = symm_mem.rendezvous(p, grp)
+            hc = symm_mem.rendezvous(c, grp)
+            self.points.append(p)
+            self.counts.append(c)
+            self._peer_pts.append([hp.get_buffer(r, (self.world * self.n_rows, 5), torch.float32)
+                                   for r in range(self.world)])
+            self._peer_cnt.append([hc.get_buffer(r, (self.world * self.n_clouds,), torch.int32)
+                                   for r in range(self.world)])
+        self._side = torch.cuda.Stream(device=self.device)
+        self._done = [torch.cuda.Event() for _ in range(self.depth)]
+        self._ready = torch.cuda.Event()
+
+    def start(self, j, points, counts):
+        """Enqueue the exchange of this rank's (points, counts) into buffer j of every rank."""
+        if self.kind == 'nccl':
+            self.pending[j] = [dist.all_gather_into_tensor(self.points[j], points, group=self.group, async_op=True),
+                               dist.all_gather_into_tensor(self.counts[j], counts, group=self.group, async_op=True)]
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self._ready.record(cur)
+        r0, r1 = self.rank * self.n_rows, (self.rank + 1) * self.n_rows
+        c0, c1 = self.rank * self.n_clouds, (self.rank + 1) * self.n_clouds
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ready)
+            for k in range(self.world):                    # start with the right-hand neighbour: spreads the NVSwitch load
+                r = (self.rank + 1 + k) % self.world
+                self._peer_pts[j][r][r0:r1].copy_(points, non_blocking=True)
+                self._peer_cnt[j][r][c0:c1].copy_(counts, non_blocking=True)
+            self._done[j].record(self._side)
+        self.pending[j] = True
+
+    def wait(self, j):
+        if self.pending[j] is None:
+            return
+        if self.kind == 'nccl':
+            for wk in self.pending[j]:
+                wk.wait()
+        else:
+            torch.cuda.current_stream(self.device).wait_event(self._done[j])
+        self.pending[j] = None
+
+    def wait_all(self):
+        for j in range(self.depth):
+            self.wait(j)

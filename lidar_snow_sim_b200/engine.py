@@ -153,13 +153,14 @@ class SnowfallEngine:
         return self._ws, need
 
     def snowfall_batch(self, table_id, points, cloud_offsets, order, beam_divergence_deg, theta=None,
-                       thresh_poly=None, noise_floor=0.7, threshold_filter=True, camera_fov=False,
+                       thresh_poly=None, plane=None, ymins=None, noise_floor=0.7, threshold_filter=True, camera_fov=False,
                        device_prepass=False, assume_sorted=False, want_full=False, want_perm=False, want_nocc=False,
                        out=None, workspace=None):
         """
         Batched augment() on device-resident clouds (enqueued on torch's current stream, no synchronisation).
 
         points: CUDA float32 (N, 5); cloud_offsets: int64 host array (B + 1); order: int32 host (B, 64).
+        plane (B,4) / ymins (B,50): optional host arrays replayed by the device pre-pass (lss_noise_threshold_poly).
         Returns dict(points=(N,5) slot-compacted rows, counts=(B,), stats=(B,4) [, full, perm, nocc]).
         Call `check()` (synchronises) to surface asynchronous device errors.
         """
@@ -184,6 +185,8 @@ class SnowfallEngine:
             tp = np.ascontiguousarray(thresh_poly, dtype=np.float64).reshape(B, 3)
         if theta is not None:
             assert theta.is_cuda and theta.dtype == torch.float32 and theta.shape[0] == N
+        pl = None if plane is None else np.ascontiguousarray(plane, dtype=np.float64).reshape(B, 4)
+        ym = None if ymins is None else np.ascontiguousarray(ymins, dtype=np.int32).reshape(B, 50)
         with torch.cuda.device(self.device):
             if out is None:
                 out = {}
@@ -204,7 +207,8 @@ class SnowfallEngine:
                 assert ws.numel() >= self.lib.lss_snowfall_workspace_bytes(N, B)
             st = self.lib.lss_snowfall_batch(
                 self.h, int(table_id), _ptr(points), _ptr(off), B, _ptr(order), float(beam_divergence_deg),
-                _ptr(theta), _ptr(tp), float(noise_floor), flags, _ptr(out['points']), _ptr(out['counts']),
+                _ptr(theta), _ptr(tp), _ptr(pl), _ptr(ym), float(noise_floor), flags, _ptr(out['points']),
+                _ptr(out['counts']),
                 _ptr(out['stats']), _ptr(out.get('full')) if want_full else None,
                 _ptr(out.get('perm')) if want_perm else None, _ptr(out.get('nocc')) if want_nocc else None,
                 _ptr(ws), int(ws.numel()), self._stream())
@@ -274,28 +278,35 @@ class SnowfallEngine:
         n = self.lib.lss_host_pipe_trace(self.h, _ptr(buf), max_chunks)
         return buf[:n]
 
-    def noise_threshold_poly(self, points, cloud_offsets, noise_floor=0.7, plane=None):
-        """Device pre-pass only: returns (poly (B,3) float64 tensor in np.polyfit order, plane (B,4) tensor).
-        plane: optional host array (B,4) = (w0, w1, w2, h) to use instead of the RANSAC estimate."""
+    def noise_threshold_poly(self, points, cloud_offsets, noise_floor=0.7, plane=None, ymins=None, want_fits=False):
+        """Device pre-pass only: returns (poly (B,3) float64 tensor in np.polyfit order, plane (B,4) tensor)
+        [, fits (B,8) float64, picks (B,50) int32 with want_fits].
+        plane: optional host array (B,4) = (w0, w1, w2, h) to use instead of the RANSAC estimate;
+        ymins: optional host int array (B,50), the reference host's np.argpartition picks (augmentation.py:236)."""
         off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
         B = off.shape[0] - 1
         N = int(off[-1])
         assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.shape == (N, 5)
         pl = None if plane is None else np.ascontiguousarray(plane, dtype=np.float64).reshape(B, 4)
+        ym = None if ymins is None else np.ascontiguousarray(ymins, dtype=np.int32).reshape(B, 50)
         with torch.cuda.device(self.device):
             need = self.lib.lss_prepass_workspace_bytes(N, B)
             ws = torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device)
             poly = torch.empty((B, 3), dtype=torch.float64, device=self.device)
             plane_out = torch.empty((B, 4), dtype=torch.float64, device=self.device)
+            fits = torch.empty((B, 8), dtype=torch.float64, device=self.device) if want_fits else None
+            picks = torch.empty((B, 50), dtype=torch.int32, device=self.device) if want_fits else None
             st = self.lib.lss_noise_threshold_poly(self.h, _ptr(points), _ptr(off), B, float(noise_floor), _ptr(pl),
-                                                   _ptr(poly), _ptr(plane_out), _ptr(ws), int(ws.numel()),
-                                                   self._stream())
+                                                   _ptr(ym), _ptr(poly), _ptr(plane_out), _ptr(fits), _ptr(picks),
+                                                   _ptr(ws), int(ws.numel()), self._stream())
         _lib.check(st, self.h)
+        if want_fits:
+            return poly, plane_out, fits, picks
         return poly, plane_out
 
     def wet_ground_batch(self, points, cloud_offsets, counts=None, water_height=0.001, pavement_depth=0.0012,
                          noise_floor=0.7, power_factor=15, flat_earth=False, delta=0.5, replace=True, plane=None,
-                         want_intensity64=False):
+                         want_intensity64=False, ymins=None):
         """
         Batched ground_water_augmentation() on device-resident clouds (current stream, no synchronisation).
         counts: optional CUDA int32 (B,) valid rows per cloud slot (fused snow -> wet path).
@@ -306,6 +317,7 @@ class SnowfallEngine:
         N = int(off[-1])
         assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.shape == (N, 5)
         pl = None if plane is None else np.ascontiguousarray(plane, dtype=np.float64).reshape(B, 4)
+        ym = None if ymins is None else np.ascontiguousarray(ymins, dtype=np.int32).reshape(B, 50)
         with torch.cuda.device(self.device):
             out = dict(points=torch.empty((N, 5), dtype=torch.float32, device=self.device),
                        counts=torch.empty((B,), dtype=torch.int32, device=self.device),
@@ -319,7 +331,7 @@ class SnowfallEngine:
             st = self.lib.lss_wet_ground_batch(
                 self.h, _ptr(points), _ptr(off), _ptr(counts), B, float(water_height), float(pavement_depth),
                 float(noise_floor), float(power_factor), 1 if flat_earth else 0, float(delta), 1 if replace else 0,
-                _ptr(pl), _ptr(out['points']), _ptr(out.get('intensity64')), _ptr(out['counts']),
+                _ptr(pl), _ptr(ym), _ptr(out['points']), _ptr(out.get('intensity64')), _ptr(out['counts']),
                 _ptr(out['passthrough']), _ptr(out['plane']), _ptr(self._ws_wet), int(self._ws_wet.numel()),
                 self._stream())
         _lib.check(st, self.h)
@@ -373,7 +385,7 @@ class SnowfallEngine:
     def kernel_times(self, reset=True):
         """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream (synchronises)."""
         torch.cuda.synchronize(self.device)
-        n = 7
+        n = 9
         ms = np.zeros(n, dtype=np.float64)
         calls = np.zeros(n, dtype=np.int64)
         _lib.check(self.lib.lss_kernel_times(self.h, 1 if reset else 0, _ptr(ms), _ptr(calls), n), self.h)

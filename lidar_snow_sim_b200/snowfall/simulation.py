@@ -12,8 +12,9 @@ Differences a caller can observe, all documented in DESIGN.md:
   * rows of one channel keep their input order (stable sort); the reference's argsort order within a channel is
     implementation-defined (simulation.py:447);
   * `show_progressbar` is accepted and ignored (it only selects the reference's process pool);
-  * keyword-only extras (`engine`, `tables`, `order`, `plane`, `thresh_poly`, `theta`) let tests inject what the
-    reference draws from global state (random.shuffle, RANSAC) or computes host-dependently (float32 arctan2).
+  * keyword-only extras (`engine`, `tables`, `order`, `plane`, `ymins`, `thresh_poly`, `theta`) let tests inject what
+    the reference draws from global state (random.shuffle, RANSAC) or computes host-dependently (float32 arctan2,
+    np.argpartition's pick among the least populated histogram bins).
 """
 import os
 import random
@@ -54,7 +55,7 @@ def _load_tables(engine, particle_file_prefix: str, root_path, max_div_rad: floa
 
 def augment(pc: np.ndarray, particle_file_prefix: str, beam_divergence: float, shuffle: bool = True,
             show_progressbar: bool = False, only_camera_fov: bool = True, noise_floor: float = 0.7,
-            root_path: str = None, *, engine=None, tables=None, order=None, plane=None, thresh_poly=None,
+            root_path: str = None, *, engine=None, tables=None, order=None, plane=None, ymins=None, thresh_poly=None,
             theta=None, return_internals: bool = False) -> Tuple:
     """
     :param pc:                      N-by-5 array containing original pointcloud (x, y, z, intensity, channel).
@@ -69,11 +70,22 @@ def augment(pc: np.ndarray, particle_file_prefix: str, beam_divergence: float, s
     """
     engine = engine or default_engine()
     max_div = float(np.radians(beam_divergence))
+    own_tables = tables is not None and not isinstance(tables, int)
     if tables is not None:
         table_id = tables if isinstance(tables, int) else engine.upload_tables(
             tables, max_beam_divergence_rad=max(max_div, DEFAULT_MAX_DIVERGENCE_RAD))
     else:
         table_id = _load_tables(engine, particle_file_prefix, root_path, max_div)
+    try:
+        return _augment_uploaded(engine, table_id, pc, beam_divergence, shuffle, only_camera_fov, noise_floor, order,
+                                 plane, ymins, thresh_poly, theta, return_internals)
+    finally:
+        if own_tables:
+            engine.free_tables(table_id)
+
+
+def _augment_uploaded(engine, table_id, pc, beam_divergence, shuffle, only_camera_fov, noise_floor, order, plane, ymins,
+                      thresh_poly, theta, return_internals):
 
     if order is None:
         order = list(range(64))
@@ -88,8 +100,12 @@ def augment(pc: np.ndarray, particle_file_prefix: str, beam_divergence: float, s
     if theta is not None:
         d_theta = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float32)).to(dev)
     off = np.array([0, n], dtype=np.int64)
+    pl = None
+    if plane is not None and thresh_poly is None:       # (w, h) as calculate_plane returns it (planes.py:50)
+        pl = np.array([[plane[0][0], plane[0][1], plane[0][2], plane[1]]], dtype=np.float64)
+    ym = None if (ymins is None or thresh_poly is not None) else np.asarray(ymins, dtype=np.int32).reshape(1, 50)
     res = engine.snowfall_batch(table_id, d_pc, off, np.asarray(order, dtype=np.int32)[None, :], float(beam_divergence),
-                                theta=d_theta, thresh_poly=thresh_poly, noise_floor=noise_floor,
+                                theta=d_theta, thresh_poly=thresh_poly, plane=pl, ymins=ym, noise_floor=noise_floor,
                                 threshold_filter=True, camera_fov=bool(only_camera_fov),
                                 device_prepass=thresh_poly is None, want_full=return_internals,
                                 want_perm=return_internals, want_nocc=return_internals)
@@ -98,8 +114,6 @@ def augment(pc: np.ndarray, particle_file_prefix: str, beam_divergence: float, s
     st = res['stats'][0].cpu().numpy()
     aug_pc = res['points'][:count].cpu().numpy()
     stats = (int(st[0]), int(st[1]), int(st[2]))
-    if tables is not None and not isinstance(tables, int):
-        engine.free_tables(table_id)
     if return_internals:
         return stats, aug_pc, dict(order=list(order), full=res['full'].cpu().numpy(), perm=res['perm'].cpu().numpy(),
                                    n_occluders=res['nocc'].cpu().numpy(), intensity_diff_sum=float(st[3]))

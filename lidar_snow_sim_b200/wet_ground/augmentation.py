@@ -12,7 +12,8 @@ CUDA engine.  Same name, arguments and return value:
 
 Notes: `debug` is accepted and ignored (it only draws matplotlib plots); estimation_method='poly' (a RANSAC polyfit
 on np.random, augmentation.py:171-192,223-228,243-246) is not implemented; coordinates are processed as float32
-(STF clouds are float32 on disk, precompute.py:78).  Keyword-only extras: `engine`, `plane`.
+(STF clouds are float32 on disk, precompute.py:78).  Keyword-only extras: `engine`, `plane`, `ymins` (the reference
+host's RANSAC plane and np.argpartition picks, replayed for parity tests).
 """
 import numpy as np
 import torch
@@ -22,7 +23,7 @@ from ..engine import default_engine
 
 def ground_water_augmentation(pointcloud, water_height=0.001, pavement_depth=0.0012, noise_floor=0.7, power_factor=15,
                               estimation_method='linear', flat_earth=False, debug=True,
-                              delta=0.5, replace=True, *, engine=None, plane=None, return_internals=False):
+                              delta=0.5, replace=True, *, engine=None, plane=None, ymins=None, return_internals=False):
     if estimation_method != 'linear':
         raise NotImplementedError("only estimation_method='linear' is implemented")
     if not isinstance(flat_earth, (bool, np.bool_)):
@@ -34,7 +35,8 @@ def ground_water_augmentation(pointcloud, water_height=0.001, pavement_depth=0.0
     pl = None if plane is None else np.asarray([[plane[0][0], plane[0][1], plane[0][2], plane[1]]], dtype=np.float64)
     res = engine.wet_ground_batch(d_pc, np.array([0, n], dtype=np.int64), None, water_height, pavement_depth,
                                   noise_floor, power_factor, bool(flat_earth), delta, bool(replace), plane=pl,
-                                  want_intensity64=True)
+                                  want_intensity64=True,
+                                  ymins=None if ymins is None else np.asarray(ymins, dtype=np.int32).reshape(1, 50))
     engine.check()
     if int(res['passthrough'][0].item()):
         return (pointcloud, dict(passthrough=True)) if return_internals else pointcloud

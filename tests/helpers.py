@@ -47,3 +47,22 @@ def augment_full_case(g):
     theta_cr = np.arctan2(pc[:, 1].astype(np.float64), pc[:, 0].astype(np.float64)).astype(np.float32)
     theta = (theta_cr.view(np.int32) + g['theta_ulp'].astype(np.int32)).view(np.float32)     # the reference host's bits
     return pc, tables, theta
+
+
+def augment_cfg1_case(g):
+    """BASELINE.json configs[1]/[2], one cloud: full 64 x 2048 cloud + 2.5 mm/h Gunn-Marshall dart-throwing tables."""
+    from lidar_snow_sim_b200.snowfall.sampling import sample_table_set
+    pc = synthetic_cloud(seed=int(g['seed']), n_azimuth=int(g['n_azimuth']), drop=float(g['drop']))
+    assert sha(pc) == str(g['cloud_sha']), 'synthetic cloud changed: regenerate tests/golden'
+    tables = sample_table_set('gunn', float(g['snowfall_rate']), float(g['terminal_velocity']), seed=int(g['table_seed']))
+    assert [t.shape[0] for t in tables] == g['table_counts'].tolist()
+    assert [sha(t) for t in tables] == [str(v) for v in g['table_sha']], 'sampler output changed (libm?): regenerate'
+    theta_cr = np.arctan2(pc[:, 1].astype(np.float64), pc[:, 0].astype(np.float64)).astype(np.float32)
+    theta = (theta_cr.view(np.int32) + g['theta_ulp'].astype(np.int32)).view(np.float32)     # the reference host's bits
+    return pc, tables, theta
+
+
+def canon_no_intensity(a):
+    """Rows ordered by (x, y, z, label) -- the key tools/make_golden.py uses for the wet-ground fixture of configs[2]."""
+    a = np.asarray(a)
+    return a[np.lexsort((a[:, 4], a[:, 2], a[:, 1], a[:, 0]))]

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import DIV, canon, channel_case, augment_case, augment_full_case, sha
+from helpers import DIV, canon, channel_case, augment_case, augment_full_case, augment_cfg1_case, canon_no_intensity, sha
 from lidar_snow_sim_b200.calib.hdl64e_s3 import sensor_arrays
 from lidar_snow_sim_b200.calib.dense_camera import STF_HDL64_CAMERA
 from lidar_snow_sim_b200.snowfall import sampling as prod_sampling
@@ -75,7 +75,7 @@ def test_augment(oracle, gold_dir, name):
     stats, aug, internals = oracle.augment(pc, tables, DIV, sensor_arrays(), order=g['order'].tolist(),
                                            plane=(g['plane_w'], float(g['plane_h'])), theta_sorted=g['theta'][idx],
                                            only_camera_fov=bool(g['fov']), calib=STF_HDL64_CAMERA, stable_sort=True,
-                                           return_internals=True)
+                                           return_internals=True, least_populated=g['ymins'])
     assert stats == tuple(int(v) for v in g['stats'])
     assert np.array_equal(canon(aug), g['out'])
     assert np.allclose(internals['thresh_poly'], g['thresh_poly'], rtol=1e-12, atol=0)
@@ -98,8 +98,32 @@ def test_wet_ground(oracle, gold_dir):
     g = np.load(os.path.join(gold_dir, 'wet_ground.npz'))
     pc = synthetic_cloud(seed=int(g['seed']), n_azimuth=int(g['n_azimuth']))
     assert sha(pc) == str(g['cloud_sha'])
-    out = oracle.ground_water_augmentation(pc, water_height=0.001, plane=(g['plane_w'], float(g['plane_h'])))
+    out = oracle.ground_water_augmentation(pc, water_height=0.001, plane=(g['plane_w'], float(g['plane_h'])),
+                                           least_populated=g['ymins'])
     assert out.dtype == np.float64 and np.array_equal(out, g['out'])
+
+
+def test_config1_and_config2(oracle, gold_dir):
+    """BASELINE.json configs[1] (2.5 mm/h Gunn-Marshall tables, full 64 x 2048 cloud) and configs[2] (snow -> wet ground):
+    the oracle, replaying the reference host's RANSAC planes / np.argpartition picks / float32 arctan2 bits, reproduces
+    the reference's own outputs."""
+    g = np.load(os.path.join(gold_dir, 'augment_cfg1.npz'))
+    pc, tables, theta = augment_cfg1_case(g)
+    idx = pc[:, 4].argsort(kind='stable')
+    stats, aug, oi = oracle.augment(pc, tables, DIV, sensor_arrays(), order=g['order'].tolist(),
+                                    plane=(g['plane_w'], float(g['plane_h'])), least_populated=g['ymins'],
+                                    theta_sorted=theta[idx], stable_sort=True, return_internals=True)
+    assert np.allclose(oi['thresh_poly'], g['thresh_poly'], rtol=1e-9, atol=0)
+    assert stats == tuple(int(v) for v in g['stats'])
+    assert aug.shape == tuple(g['out_shape']) and sha(canon(aug)) == str(g['out_sha'])
+    wet = oracle.ground_water_augmentation(aug, water_height=0.001, replace=False,
+                                           plane=(g['wet_plane_w'], float(g['wet_plane_h'])),
+                                           least_populated=g['wet_ymins'])
+    assert wet.shape == tuple(g['wet_shape'])
+    wc = canon_no_intensity(wet)
+    assert sha(wc[:, [0, 1, 2, 4]]) == str(g['wet_xyzl_sha'])
+    assert np.allclose(wc[:, 3], g['wet_intensity'], rtol=1e-12, atol=0)
+    assert [(wet[:, 4] == l).sum() for l in (0, 1, 2)] == g['wet_label_counts'].tolist()
 
 
 def test_dart_throwing(oracle, gold_dir):

@@ -55,6 +55,56 @@ def write_tables(root, prefix, tables):
         np.save(os.path.join(d, f'{prefix}_{k + 1}.npy'), t)
 
 
+class CapturePrepass:
+    """Records, while the unmodified reference runs, the library-defined choices of its pre-pass so that they can be
+    replayed on the device: the RANSAC plane (planes.py:35), the np.argpartition picks (augmentation.py:236), the two
+    linregress fits (:216, :249) and the np.polyfit result (simulation.py:467)."""
+
+    def __init__(self, ns):
+        self.ns = ns
+        self.planes, self.ymins, self.fits, self.polys = [], [], [], []
+
+    def __enter__(self):
+        ns = self.ns
+        self._cp_sim, self._cp_wet = ns.sim.calculate_plane, ns.wet_aug.calculate_plane
+        self._argpart, self._polyfit, self._linreg = np.argpartition, np.polyfit, ns.wet_aug.linregress
+        cap = self
+
+        def cp(p, *a, **k):
+            w, h = cap._cp_wet(p, *a, **k)
+            cap.planes.append((np.asarray(w, dtype=np.float64), float(h)))
+            return w, h
+
+        def ap(a, kth, axis=-1, *r, **k):
+            out = cap._argpart(a, kth, axis, *r, **k)
+            if getattr(a, 'shape', None) == (50, 2555) and kth == 2 and axis == 1:
+                cap.ymins.append(np.asarray(out[:, 0], dtype=np.int32).copy())
+            return out
+
+        def pf(x, y, deg, *a, **k):
+            r = cap._polyfit(x, y, deg, *a, **k)
+            cap.polys.append(np.asarray(r, dtype=np.float64))
+            return r
+
+        def lr(x, y=None, *a, **k):
+            r = cap._linreg(x, y, *a, **k)
+            cap.fits.append((float(r[0]), float(r[1])))
+            return r
+
+        ns.sim.calculate_plane = cp
+        ns.wet_aug.calculate_plane = cp
+        np.argpartition = ap
+        np.polyfit = pf
+        ns.wet_aug.linregress = lr
+        return self
+
+    def __exit__(self, *exc):
+        ns = self.ns
+        ns.sim.calculate_plane, ns.wet_aug.calculate_plane = self._cp_sim, self._cp_wet
+        np.argpartition, np.polyfit, ns.wet_aug.linregress = self._argpart, self._polyfit, self._linreg
+        return False
+
+
 def main():
     ns = rh.load()
     os.makedirs(GOLD, exist_ok=True)
@@ -159,30 +209,12 @@ def main():
         tables = [synthetic_particles(5000 + 64 * seed + k, n_part) for k in range(64)]
         root = tempfile.mkdtemp()
         write_tables(root, 'g', tables)
-        cap = {}
-        orig_cp = ns.sim.calculate_plane
-        orig_polyfit = np.polyfit
-
-        def cp(p):
-            w, h = orig_cp(p)
-            cap['plane'] = (np.asarray(w, dtype=np.float64), float(h))
-            return w, h
-
-        def pf(x, y, deg, *a, **k):
-            r = orig_polyfit(x, y, deg, *a, **k)
-            cap['poly'] = np.asarray(r, dtype=np.float64)
-            return r
-
-        ns.sim.calculate_plane = cp
-        np.polyfit = pf
-        try:
+        with CapturePrepass(ns) as cp_:
             random.seed(seed)
             np.random.seed(seed)
             stats, aug = ns.sim.augment(pc, 'g', DIV, shuffle=True, show_progressbar=True, only_camera_fov=fov,
                                         root_path=root)
-        finally:
-            ns.sim.calculate_plane = orig_cp
-            np.polyfit = orig_polyfit
+        cap = {'plane': cp_.planes[0], 'poly': cp_.polys[0], 'ymins': cp_.ymins[0], 'fits': np.array(cp_.fits[:2])}
         random.seed(seed)
         order = list(range(64))
         random.shuffle(order)
@@ -203,8 +235,8 @@ def main():
                             drop=0.08 if seed else 0.0, shuffle_rows=bool(seed), fov=fov,
                             cloud_sha=sha(pc), table_sha=np.array([sha(t) for t in tables]),
                             order=np.array(order, dtype=np.int32), plane_w=cap['plane'][0], plane_h=cap['plane'][1],
-                            thresh_poly=cap['poly'], theta=theta_orig, stats=np.array(stats, dtype=np.int64),
-                            out=canon(aug))
+                            thresh_poly=cap['poly'], ymins=cap['ymins'], fits=cap['fits'], theta=theta_orig,
+                            stats=np.array(stats, dtype=np.int64), out=canon(aug))
 
     # ---------------------------------------------------------------- FULL-SIZE augment: 64 x 2048 cloud, dart-throwing tables
     # (BASELINE.json configs[0]).  Only hashes / small arrays are stored: the cloud and the tables are regenerated from
@@ -214,29 +246,11 @@ def main():
     tables = sample_table_set('gunn', 1.0, 1.6, seed=1000)
     root = tempfile.mkdtemp()
     write_tables(root, 'g', tables)
-    cap = {}
-    orig_cp = ns.sim.calculate_plane
-    orig_polyfit = np.polyfit
-
-    def cp3(p):
-        w, h = orig_cp(p)
-        cap['plane'] = (np.asarray(w, dtype=np.float64), float(h))
-        return w, h
-
-    def pf3(x, y, deg, *a, **k):
-        r = orig_polyfit(x, y, deg, *a, **k)
-        cap['poly'] = np.asarray(r, dtype=np.float64)
-        return r
-
-    ns.sim.calculate_plane = cp3
-    np.polyfit = pf3
-    try:
+    with CapturePrepass(ns) as cp_:
         random.seed(7)
         np.random.seed(7)
         stats, aug = ns.sim.augment(pc, 'g', DIV, shuffle=True, show_progressbar=True, only_camera_fov=False, root_path=root)
-    finally:
-        ns.sim.calculate_plane = orig_cp
-        np.polyfit = orig_polyfit
+    cap = {'plane': cp_.planes[0], 'poly': cp_.polys[0], 'ymins': cp_.ymins[0], 'fits': np.array(cp_.fits[:2])}
     random.seed(7)
     order = list(range(64))
     random.shuffle(order)
@@ -255,31 +269,75 @@ def main():
     np.savez_compressed(os.path.join(GOLD, 'augment_full.npz'), seed=0, n_azimuth=2048, drop=0.08, cloud_sha=sha(pc),
                         table_sha=np.array([sha(t) for t in tables]), table_counts=np.array([t.shape[0] for t in tables]),
                         order=np.array(order, dtype=np.int32), plane_w=cap['plane'][0], plane_h=cap['plane'][1],
-                        thresh_poly=cap['poly'], theta_ulp=ulp.astype(np.int8), stats=np.array(stats, dtype=np.int64),
+                        thresh_poly=cap['poly'], ymins=cap['ymins'], fits=cap['fits'], theta_ulp=ulp.astype(np.int8),
+                        stats=np.array(stats, dtype=np.int64),
                         out_sha=sha(canon(aug)), out_shape=np.array(aug.shape),
                         label_counts=np.array([(aug[:, 4] == l).sum() for l in (0, 1, 2)]),
                         label_counts_unfiltered=np.array([(o_int['full'][:, 4] == l).sum() for l in (0, 1, 2)]))
 
+    # ---------------------------------------------------------------- BASELINE.json configs[1] / configs[2], one cloud each:
+    # 64 x 2048 cloud (no drop), 2.5 mm/h Gunn-Marshall dart-throwing tables; then the wet-ground model on the snow
+    # output the way the viewer chains them (pointcloud_viewer.py:2804-2821: replace=False).  Stored: hashes, the
+    # pre-pass choices of both stages, and the wet stage's float64 intensities in canonical row order.
+    pc = synthetic_cloud(seed=1, n_azimuth=2048)
+    tables = sample_table_set('gunn', 2.5, 1.6, seed=1000)
+    root = tempfile.mkdtemp()
+    write_tables(root, 'g', tables)
+    with CapturePrepass(ns) as cp_:
+        random.seed(11)
+        np.random.seed(11)
+        stats, aug = ns.sim.augment(pc, 'g', DIV, shuffle=True, show_progressbar=True, only_camera_fov=False, root_path=root)
+    cap = {'plane': cp_.planes[0], 'poly': cp_.polys[0], 'ymins': cp_.ymins[0], 'fits': np.array(cp_.fits[:2])}
+    random.seed(11)
+    order = list(range(64))
+    random.shuffle(order)
+    theta = np.arctan2(pc[:, 1], pc[:, 0])
+    theta_cr = np.arctan2(pc[:, 1].astype(np.float64), pc[:, 0].astype(np.float64)).astype(np.float32)
+    ulp = (theta.view(np.int32).astype(np.int64) - theta_cr.view(np.int32).astype(np.int64))
+    assert np.abs(ulp).max() < 100
+    idx = pc[:, 4].argsort(kind='stable')
+    o_stats, o_aug, o_int = orc.augment(pc, tables, DIV, sensor, order=order, plane=cap['plane'],
+                                        theta_sorted=theta[idx], stable_sort=True, return_internals=True)
+    stats = tuple(int(v) for v in stats)
+    good = (stats == o_stats) and aug.shape == o_aug.shape and np.array_equal(canon(aug), canon(o_aug))
+    good_poly = np.allclose(o_int['thresh_poly'], cap['poly'], rtol=1e-12, atol=0)
+    print(f'augment_cfg1: oracle==reference: {good} (poly match {good_poly}) stats {stats} out {aug.shape} labels',
+          [(aug[:, 4] == l).sum() for l in (0, 1, 2)])
+    ok &= good and good_poly
+    with CapturePrepass(ns) as cw_:
+        np.random.seed(12)
+        wet = ns.wet_aug.ground_water_augmentation(aug, water_height=0.001, debug=False, replace=False)
+    o_wet = orc.ground_water_augmentation(aug, water_height=0.001, replace=False, plane=cw_.planes[0])
+    good = wet.shape == o_wet.shape and np.array_equal(wet, o_wet)
+    print('snow -> wet (cfg2): oracle==reference:', good, wet.shape, 'kept ground', int((wet[:, 4] == 1).sum()))
+    ok &= good
+    wkey = np.lexsort((wet[:, 4], wet[:, 2], wet[:, 1], wet[:, 0]))          # canonical order WITHOUT the intensity column
+    wet_c = wet[wkey]
+    np.savez_compressed(os.path.join(GOLD, 'augment_cfg1.npz'), seed=1, n_azimuth=2048, drop=0.0, cloud_sha=sha(pc),
+                        snowfall_rate=2.5, terminal_velocity=1.6, table_seed=1000,
+                        table_sha=np.array([sha(t) for t in tables]), table_counts=np.array([t.shape[0] for t in tables]),
+                        order=np.array(order, dtype=np.int32), plane_w=cap['plane'][0], plane_h=cap['plane'][1],
+                        thresh_poly=cap['poly'], ymins=cap['ymins'], fits=cap['fits'], theta_ulp=ulp.astype(np.int8),
+                        stats=np.array(stats, dtype=np.int64), out_sha=sha(canon(aug)), out_shape=np.array(aug.shape),
+                        label_counts=np.array([(aug[:, 4] == l).sum() for l in (0, 1, 2)]),
+                        label_counts_unfiltered=np.array([(o_int['full'][:, 4] == l).sum() for l in (0, 1, 2)]),
+                        wet_plane_w=cw_.planes[0][0], wet_plane_h=cw_.planes[0][1], wet_ymins=cw_.ymins[0],
+                        wet_fits=np.array(cw_.fits[:2]), wet_shape=np.array(wet.shape),
+                        wet_xyzl_sha=sha(wet_c[:, [0, 1, 2, 4]]), wet_intensity=wet_c[:, 3],
+                        wet_label_counts=np.array([(wet[:, 4] == l).sum() for l in (0, 1, 2)]))
+
     # ---------------------------------------------------------------- wet ground (wet_ground/augmentation.py:25-161)
     pc = synthetic_cloud(seed=3, n_azimuth=256)
-    cap = {}
-    orig_cp = ns.wet_aug.calculate_plane
-
-    def cp2(p):
-        w, h = orig_cp(p)
-        cap['plane'] = (np.asarray(w, dtype=np.float64), float(h))
-        return w, h
-
-    ns.wet_aug.calculate_plane = cp2
-    np.random.seed(3)
-    wet = ns.wet_aug.ground_water_augmentation(pc, water_height=0.001, debug=False)
-    ns.wet_aug.calculate_plane = orig_cp
+    with CapturePrepass(ns) as cp_:
+        np.random.seed(3)
+        wet = ns.wet_aug.ground_water_augmentation(pc, water_height=0.001, debug=False)
+    cap = {'plane': cp_.planes[0], 'ymins': cp_.ymins[0], 'fits': np.array(cp_.fits[:2])}
     o_wet = orc.ground_water_augmentation(pc, water_height=0.001, plane=cap['plane'])
     good = wet.shape == o_wet.shape and np.array_equal(wet, o_wet)
     print('wet ground: oracle==reference:', good, wet.shape, wet.dtype)
     ok &= good
     np.savez_compressed(os.path.join(GOLD, 'wet_ground.npz'), seed=3, n_azimuth=256, cloud_sha=sha(pc),
-                        plane_w=cap['plane'][0], plane_h=cap['plane'][1], out=wet)
+                        plane_w=cap['plane'][0], plane_h=cap['plane'][1], ymins=cap['ymins'], fits=cap['fits'], out=wet)
 
     # ---------------------------------------------------------------- dart throwing (sampling.py:90-194)
     occ = float(ns.sampling.compute_occupancy(2.5, 1.6))
