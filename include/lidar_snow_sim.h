@@ -245,6 +245,34 @@ LSS_API lss_status lss_fog_batch(lss_engine *e, const float *d_points, int n_fea
                                  double *d_out_info, void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_fog_workspace_bytes(int64_t n_total, int n_clouds);
 
+/* ---- point-range mask + voxelisation ("next" row) ---------------------------------------------------------
+ * The detector-input stage of the reference's data path on device-resident clouds, e.g. the slot-compacted output of
+ * lss_snowfall_batch / lss_wet_ground_batch, so that the augmented batch reaches the detector without a host round trip:
+ *   DataProcessor.mask_points_and_boxes_outside_range (points part)   lib/OpenPCDet/pcdet/datasets/processor/data_processor.py:78-91
+ *       = mask_points_by_range, lib/OpenPCDet/pcdet/utils/common_utils.py:60-63: x and y inside the range, ends inclusive
+ *   DataProcessor.transform_points_to_voxels                             data_processor.py:115-143 -> VoxelGeneratorWrapper
+ *       (:15-58) -> spconv's point-to-voxel rule (third party; restated in oracle/voxel.py): float32
+ *       c = floor((p - range_min) / voxel_size), points outside the grid skipped, voxels numbered by first appearance in
+ *       point order, at most max_voxels voxels, the first max_points_per_voxel points of a voxel kept in point order
+ *   batch index column of DatasetTemplate.collate_batch                  lib/OpenPCDet/pcdet/datasets/dataset.py:199-204
+ *
+ *   d_points            float32[n_total * n_features], n_features >= 3 (x, y, z, ...); cloud b starts at row h_cloud_offsets[b]
+ *   d_cloud_counts      int32[n_clouds] device or NULL: valid rows per cloud slot (slot-compacted input)
+ *   h_point_cloud_range float32[6] (x0, y0, z0, x1, y1, z1); h_voxel_size float32[3]     (dense_dataset.yaml:4,71)
+ *   mask_xy_range       != 0: apply the x / y range mask first (it differs from the grid test at the upper edge)
+ *   d_out_voxels        float32[n_clouds * max_voxels * max_points_per_voxel * n_features], zero padded
+ *   d_out_coords        int32[n_clouds * max_voxels * 4]   (cloud index, z, y, x)
+ *   d_out_num_points    int32[n_clouds * max_voxels]
+ *   d_out_n_voxels      int32[n_clouds]; cloud b's voxels are rows [0, n_voxels[b]) of its slot of max_voxels rows
+ * Results are bit-identical to the sequential rule (integer reductions only).                                           */
+LSS_API lss_status lss_voxelize_batch(lss_engine *e, const float *d_points, int n_features, const int64_t *h_cloud_offsets,
+                                      const int32_t *d_cloud_counts, int n_clouds, const float *h_point_cloud_range,
+                                      const float *h_voxel_size, int max_points_per_voxel, int max_voxels,
+                                      int mask_xy_range, float *d_out_voxels, int32_t *d_out_coords,
+                                      int32_t *d_out_num_points, int32_t *d_out_n_voxels, void *d_workspace,
+                                      int64_t workspace_bytes, void *stream);
+LSS_API int64_t lss_voxelize_workspace_bytes(int64_t n_total, int n_clouds, int max_points_per_voxel, int max_voxels);
+
 /* ---- snowflake table sampler ---------------------------------------------------------------------------------------
  * dart_throwing(occupancy_ratio, precipitation_rate, R_0, rng, distribution) of tools/snowfall/sampling.py:90-194:
  * sequential rejection sampling of non-overlapping disks in a disk of radius R_0 until the occupied area reaches

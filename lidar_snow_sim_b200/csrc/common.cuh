@@ -180,7 +180,7 @@ inline cudaError_t lss_zero_async(lss_engine *e, const ZeroRegions &r, cudaStrea
 }
 
 enum { LSS_K_SORT = 0, LSS_K_PREPASS = 1, LSS_K_SNOWFALL = 2, LSS_K_COMPACT = 3, LSS_K_FINALIZE = 4, LSS_K_WET = 5,
-       LSS_K_FOG = 6, LSS_K_SCAN = 7, LSS_K_SOLVE = 8, LSS_K_COUNT = 9 };   // 7, 8: inside the LSS_K_SNOWFALL bracket
+       LSS_K_FOG = 6, LSS_K_SCAN = 7, LSS_K_SOLVE = 8, LSS_K_VOXEL = 9, LSS_K_COUNT = 10 };   // 7, 8: inside the LSS_K_SNOWFALL bracket
 
 struct KernelTimer {        // RAII: records begin/end events when profiling is on
     lss_engine *e; cudaStream_t s; int idx = -1;

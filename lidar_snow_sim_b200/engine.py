@@ -371,6 +371,38 @@ class SnowfallEngine:
         _lib.check(st, self.h)
         return out
 
+    def voxelize_batch(self, points, cloud_offsets, point_cloud_range, voxel_size, max_points_per_voxel, max_voxels,
+                       counts=None, mask_xy_range=True):
+        """
+        Batched point-range mask + voxelisation (DataProcessor.mask_points_and_boxes_outside_range +
+        transform_points_to_voxels, lib/OpenPCDet/pcdet/datasets/processor/data_processor.py:78-91,115-143) on
+        device-resident clouds (current stream, no synchronisation).  points: CUDA float32 (N, F); counts: optional CUDA
+        int32 (B,) valid rows per cloud slot.  Returns dict(voxels (B, max_voxels, max_points, F) float32, coords
+        (B, max_voxels, 4) int32 = (cloud, z, y, x), num_points (B, max_voxels) int32, n_voxels (B,) int32).
+        """
+        off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
+        B = off.shape[0] - 1
+        N = int(off[-1])
+        assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous() and points.shape[0] == N
+        F = int(points.shape[1])
+        rng = np.ascontiguousarray(point_cloud_range, dtype=np.float32).reshape(6)
+        vs = np.ascontiguousarray(voxel_size, dtype=np.float32).reshape(3)
+        T, MV = int(max_points_per_voxel), int(max_voxels)
+        with torch.cuda.device(self.device):
+            out = dict(voxels=torch.empty((B, MV, T, F), dtype=torch.float32, device=self.device),
+                       coords=torch.empty((B, MV, 4), dtype=torch.int32, device=self.device),
+                       num_points=torch.empty((B, MV), dtype=torch.int32, device=self.device),
+                       n_voxels=torch.empty((B,), dtype=torch.int32, device=self.device))
+            need = self.lib.lss_voxelize_workspace_bytes(N, B, T, MV)
+            if getattr(self, '_ws_vox', None) is None or self._ws_vox.numel() < need:
+                self._ws_vox = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            st = self.lib.lss_voxelize_batch(self.h, _ptr(points), F, _ptr(off), _ptr(counts), B, _ptr(rng), _ptr(vs), T, MV,
+                                             1 if mask_xy_range else 0, _ptr(out['voxels']), _ptr(out['coords']),
+                                             _ptr(out['num_points']), _ptr(out['n_voxels']), _ptr(self._ws_vox),
+                                             int(self._ws_vox.numel()), self._stream())
+        _lib.check(st, self.h)
+        return out
+
     def check(self):
         """Synchronise the current stream and raise the exception type the reference would have raised."""
         with torch.cuda.device(self.device):
@@ -385,7 +417,7 @@ class SnowfallEngine:
     def kernel_times(self, reset=True):
         """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream (synchronises)."""
         torch.cuda.synchronize(self.device)
-        n = 9
+        n = 10
         ms = np.zeros(n, dtype=np.float64)
         calls = np.zeros(n, dtype=np.int64)
         _lib.check(self.lib.lss_kernel_times(self.h, 1 if reset else 0, _ptr(ms), _ptr(calls), n), self.h)

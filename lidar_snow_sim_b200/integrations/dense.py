@@ -20,6 +20,11 @@ import numpy as np
 from ..engine import default_engine
 from ..fog.simulation import ParameterSet, simulate_fog
 from ..snowfall.precompute import SNOWFALL_RATES, TERMINAL_VELOCITIES, get_fov_flag
+
+# the (snowfall_rate, terminal_velocity) pairs DenseDataset draws its rain rate from (dense_dataset.py:91-92): eight
+# entries, whose rain rates truncate to 2, 4, 8, 17, 34, 70, 130, 200 mm/h
+DATASET_SNOWFALL_RATES = [0.5, 0.5, 1.0, 2.0, 2.5, 1.5, 1.5, 1.0]
+DATASET_TERMINAL_VELOCITIES = [2.0, 1.2, 1.6, 2.0, 1.6, 0.6, 0.4, 0.2]
 from ..snowfall.sampling import snowfall_rate_to_rainfall_rate
 from ..snowfall.simulation import augment
 from ..wet_ground.augmentation import ground_water_augmentation
@@ -29,15 +34,34 @@ _CHANCES = {'8in9': [1, 1, 1, 1, 1, 1, 1, 1, 0], '4in5': [1, 1, 1, 1, 0], '1in2'
 
 
 class OnTheFlyWeather:
-    def __init__(self, dataset_cfg, rainfall_rates=None, engine=None, table_seed=42):
+    def __init__(self, dataset_cfg, rainfall_rates=None, engine=None, table_seed=42, only_precomputed=False):
+        """rainfall_rates: the list `int(np.random.choice(...))` draws from; default = the reference's own eight rain
+        rates (dense_dataset.py:91-102), so 'uniform' sampling has the reference's distribution and consumes NumPy's
+        global RNG identically.  The drawn value is truncated to the integer the pre-computed folders are named after
+        (precompute.py:88-89) and mapped back to its (snowfall_rate, terminal_velocity) pair: precompute.py's five
+        pairs first (what the file would have contained), then the dataset's eight.  The reference finds no file for
+        the three rates precompute.py does not produce and skips the augmentation with a message; here they are
+        computed on the fly unless `only_precomputed`."""
         self.cfg = dataset_cfg
         self.engine = engine
         self.table_seed = table_seed
-        # the integer rain rates the pre-computed folders are named after (precompute.py:57,88-89)
         self.pairs = {}
-        for rs, tv in zip(SNOWFALL_RATES, TERMINAL_VELOCITIES):
-            self.pairs[int(snowfall_rate_to_rainfall_rate(rs, tv))] = (rs, tv)
-        self.rainfall_rates = list(rainfall_rates) if rainfall_rates is not None else sorted(self.pairs)
+
+        def register(rates, velocities):
+            for rs, tv in zip(rates, velocities):
+                key = int(snowfall_rate_to_rainfall_rate(rs, tv))
+                if key in self.pairs and self.pairs[key] != (rs, tv):
+                    raise ValueError(f'rain rates of {self.pairs[key]} and {(rs, tv)} both truncate to {key} mm/h: '
+                                     f'the folder name rainrate_{key} would be ambiguous')
+                self.pairs.setdefault(key, (rs, tv))
+
+        register(SNOWFALL_RATES, TERMINAL_VELOCITIES)
+        if not only_precomputed:
+            register(DATASET_SNOWFALL_RATES, DATASET_TERMINAL_VELOCITIES)
+        if rainfall_rates is None:
+            rainfall_rates = [snowfall_rate_to_rainfall_rate(rs, tv)
+                              for rs, tv in zip(DATASET_SNOWFALL_RATES, DATASET_TERMINAL_VELOCITIES)]
+        self.rainfall_rates = list(rainfall_rates)
         self._tables = {}
 
     def _engine(self):
@@ -71,7 +95,7 @@ class OnTheFlyWeather:
                     _, points = augment(pc, '', float(np.degrees(3e-3)), engine=self._engine(), tables=tid)
                     snowfall_augmentation_applied = True
                 except FileNotFoundError as exc:                                       # dense_dataset.py:784-786
-                    print(f'\\n{exc}')
+                    print(f'\n{exc}')
         if training and 'WET_SURFACE' in cfg:
             method = cfg['WET_SURFACE']
             choices = [0]

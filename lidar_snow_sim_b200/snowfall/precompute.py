@@ -86,7 +86,7 @@ def precompute(sample_ids, lidar_folder, modes=('gunn', 'sekhon'), npy_root=None
                     progress(mode, rain, len(ids_j))
                 return len(ids_j)
 
-            pending = None
+            pending = in_flight = None
             try:
                 # double buffered: while the GPU works on batch k, the host reads the files of batch k+1 and writes
                 # those of batch k-1
@@ -107,18 +107,24 @@ def precompute(sample_ids, lidar_folder, modes=('gunn', 'sekhon'), npy_root=None
                     ticket = engine.snowfall_batch_host_submit(tid, host, off, np.asarray(orders, dtype=np.int32), div_deg,
                                                                device_prepass=True, camera_fov=only_camera_fov,
                                                                n_chunks=min(4, len(ids)))
-                    if pending is not None:
-                        job, pending = pending, None
-                        written += finish(job)
-                    pending = (ticket, ids, off)
+                    # the new ticket is tracked BEFORE the previous batch is finished: if writing that one raises, the
+                    # `finally` below still waits for both before the tables are freed
+                    previous, pending = pending, (ticket, ids, off)
+                    if previous is not None:
+                        in_flight = previous
+                        written += finish(previous)
+                        in_flight = None
                 if pending is not None:
                     job, pending = pending, None
+                    in_flight = job
                     written += finish(job)
+                    in_flight = None
             finally:
-                if pending is not None:                              # an exception above: do not leave a batch in flight
-                    try:
-                        engine.snowfall_batch_host_wait(pending[0])
-                    except Exception:
-                        pass
+                for job in (in_flight, pending):                     # an exception above: leave no batch in flight
+                    if job is not None:
+                        try:
+                            engine.snowfall_batch_host_wait(job[0])
+                        except Exception:
+                            pass
                 engine.free_tables(tid)
     return written

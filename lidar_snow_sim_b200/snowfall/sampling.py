@@ -121,3 +121,56 @@ def sample_table_set(mode: str, snowfall_rate: float, terminal_velocity: float, 
         _lib.check(rc)
         break
     return [out[k, :counts[k]].copy() for k in range(n_planes)]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# persistent table cache with the reference's file naming
+# ----------------------------------------------------------------------------------------------------------------------
+def table_dir(root_path=None):
+    """Directory of the particle files, as augment() looks them up (tools/snowfall/simulation.py:324-327):
+    '<root_path>/training/snowflakes/npy' or '<repo>/npy' (override: environment variable LSS_NPY_DIR)."""
+    import os
+    from pathlib import Path
+    if root_path:
+        return Path(root_path) / 'training' / 'snowflakes' / 'npy'
+    return Path(os.environ.get('LSS_NPY_DIR', Path(__file__).parent.parent.parent.absolute() / 'npy'))
+
+
+def table_files(prefix: str, directory, n_planes: int = 64):
+    """'<dist>_<rate>_<ratio>_<line>.npy', line = 1 .. 64 (sampling.py:344, simulation.py:78)."""
+    from pathlib import Path
+    return [Path(directory) / f'{prefix}_{k}.npy' for k in range(1, n_planes + 1)]
+
+
+def load_table_set(prefix: str, directory):
+    """The 64 (x, y, r) float64 tables of one prefix; FileNotFoundError like np.load in the reference (simulation.py:329)."""
+    tabs = []
+    for path in table_files(prefix, directory):
+        if not path.is_file():
+            raise FileNotFoundError(f"[Errno 2] No such file or directory: '{path}'")
+        tabs.append(np.load(str(path)))
+    return tabs
+
+
+def load_or_sample_table_set(mode: str, snowfall_rate: float, terminal_velocity: float, root_path=None, directory=None,
+                             write: bool = False, seed: int = 1000, R_0: float = 80.0):
+    """
+    The table set of (mode, snowfall_rate, terminal_velocity): read from '<prefix>_<k>.npy' if all 64 files exist (the
+    reference's published tables, or files written earlier), else drawn by the native sampler (plane k from
+    np.random.default_rng(seed + k)) and -- with `write` -- saved under the reference's names, skipping files that
+    exist (sampling.py:346-347).  Returns (tables, prefix, 'files' | 'sampled').
+    """
+    prefix = particle_file_prefix(mode, snowfall_rate, terminal_velocity)
+    directory = table_dir(root_path) if directory is None else directory
+    files = table_files(prefix, directory)
+    if all(f.is_file() for f in files):
+        return [np.load(str(f)) for f in files], prefix, 'files'
+    if mode not in _DIST:
+        raise NotImplementedError('Distribution model unknown.')
+    tables = sample_table_set(mode, snowfall_rate, terminal_velocity, seed=seed, R_0=R_0)
+    if write:
+        files[0].parent.mkdir(parents=True, exist_ok=True)
+        for f, t in zip(files, tables):
+            if not f.is_file():
+                np.save(str(f), t)
+    return tables, prefix, 'sampled'

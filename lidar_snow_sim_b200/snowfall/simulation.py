@@ -25,26 +25,20 @@ import numpy as np
 import torch
 
 from ..engine import default_engine, DEFAULT_MAX_DIVERGENCE_RAD
+from .sampling import table_dir, load_table_set, load_or_sample_table_set, particle_file_prefix
 
 _table_cache = {}
 
 
-def _load_tables(engine, particle_file_prefix: str, root_path, max_div_rad: float):
-    """Particle-table lookup of simulation.py:324-329, cached per (engine, directory, prefix)."""
-    if root_path:
-        base = Path(root_path) / 'training' / 'snowflakes' / 'npy'
-    else:
-        base = Path(os.environ.get('LSS_NPY_DIR', Path(__file__).parent.parent.parent.absolute() / 'npy'))
+def _load_tables(engine, particle_file_prefix: str, root_path, max_div_rad: float, tables=None):
+    """Particle-table lookup of simulation.py:324-329, uploaded once and cached per (engine, directory, prefix)."""
+    base = table_dir(root_path)
     key = (id(engine), str(base), particle_file_prefix)
     hit = _table_cache.get(key)
     if hit is not None and hit[1] >= max_div_rad:
         return hit[0]
-    tables = []
-    for k in range(1, 65):
-        path = base / f'{particle_file_prefix}_{k}.npy'
-        if not path.is_file():
-            raise FileNotFoundError(f"[Errno 2] No such file or directory: '{path}'")
-        tables.append(np.load(str(path)))
+    if tables is None:
+        tables = load_table_set(particle_file_prefix, base)
     if hit is not None:
         engine.free_tables(hit[0])
     build_div = max(max_div_rad, DEFAULT_MAX_DIVERGENCE_RAD)
@@ -118,3 +112,34 @@ def _augment_uploaded(engine, table_id, pc, beam_divergence, shuffle, only_camer
         return stats, aug_pc, dict(order=list(order), full=res['full'].cpu().numpy(), perm=res['perm'].cpu().numpy(),
                                    n_occluders=res['nocc'].cpu().numpy(), intensity_diff_sum=float(st[3]))
     return stats, aug_pc
+
+
+def augment_snowfall(pc: np.ndarray, snowfall_rate: float, terminal_velocity: float = 1.6, mode: str = 'gunn',
+                     beam_divergence: float = float(np.degrees(3e-3)), shuffle: bool = True,
+                     show_progressbar: bool = False, only_camera_fov: bool = True, noise_floor: float = 0.7,
+                     root_path: str = None, *, engine=None, write_tables: bool = False, table_seed: int = 1000,
+                     **extras) -> Tuple:
+    """
+    augment() addressed by the physical parameters instead of a particle-file prefix:
+
+        stats, aug_pc = augment_snowfall(pc, snowfall_rate=2.5, terminal_velocity=1.6, mode='gunn')
+
+    Derives the prefix '<mode>_<rain_rate>_<occupancy>' exactly like the reference's callers do
+    (tools/snowfall/precompute.py:57-58,101, pointcloud_viewer.py:2798-2802), reads '<prefix>_<1..64>.npy' from the
+    directory augment() would read them from if they are all there, and otherwise draws the 64 planes with the engine's
+    native dart-throwing sampler (no 2.3 GB download; `write_tables=True` stores them under the reference's file names,
+    sampling.py:344, so that the next process -- or the reference itself -- finds them).  The table set is uploaded once
+    per process and engine.  Everything else is augment(): same defaults (beam_divergence = degrees(3e-3),
+    precompute.py:104), same return value, same exceptions; `extras` are augment()'s keyword-only test hooks.
+    """
+    engine = engine or default_engine()
+    prefix = particle_file_prefix(mode, snowfall_rate, terminal_velocity)
+    key = (id(engine), str(table_dir(root_path)), prefix)
+    max_div = float(np.radians(beam_divergence))
+    hit = _table_cache.get(key)
+    if hit is None or hit[1] < max_div:
+        tables, _, _ = load_or_sample_table_set(mode, snowfall_rate, terminal_velocity, root_path=root_path,
+                                                write=write_tables, seed=table_seed)
+        _load_tables(engine, prefix, root_path, max_div, tables=tables)
+    return augment(pc, prefix, beam_divergence, shuffle=shuffle, show_progressbar=show_progressbar,
+                   only_camera_fov=only_camera_fov, noise_floor=noise_floor, root_path=root_path, engine=engine, **extras)

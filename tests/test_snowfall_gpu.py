@@ -413,3 +413,72 @@ def test_degenerate_rows(engine, oracle, tables18k):
     same = np.isnan(want) & np.isnan(got) | (want == got)
     assert same.all()
     engine.free_tables(tid)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (4) many occluders on one beam: the solve kernel's deferral to the overflow kernel, and the hard cap
+# ----------------------------------------------------------------------------------------------------------------------
+def _column_of_flakes(n, seed):
+    """n small disks strung along azimuth ~0 between 2 and 45 m, plus background flakes elsewhere."""
+    rng = np.random.default_rng(seed)
+    r = np.sort(rng.uniform(10.0, 28.0, n))
+    col = np.column_stack((r, rng.uniform(-1.2e-3, 1.2e-3, n) * r, rng.uniform(1e-4, 3e-4, n)))    # ~1e-5 rad wide each
+    return np.vstack((col, synthetic_particles(seed, 3000)))
+
+
+def test_beams_with_dozens_of_occluders_match_the_oracle(engine, oracle):
+    """40 and 100 occluders on one beam: more than the solve kernel's shared-memory arena takes per beam (63), so the
+    second case is deferred to the overflow kernel -- both must equal the oracle (labels, intensities, occluder counts)."""
+    fd, fs, mi, mx = sensor_arrays()
+    for n_col, seed in ((40, 21), (100, 22)):
+        table = _column_of_flakes(n_col, seed)
+        az = np.concatenate(([0.0, 1e-4, -2e-4, 3e-4], np.linspace(-np.pi, np.pi, 60, endpoint=False)))
+        d = np.concatenate(([50.0, 48.0, 60.0, 30.0], np.full(60, 35.0)))
+        pts = np.stack([d * np.cos(az), d * np.sin(az), np.zeros_like(d), np.full_like(d, 90.0), np.full_like(d, 5.0)],
+                       axis=1).astype(np.float32)
+        theta = np.arctan2(pts[:, 1], pts[:, 0])
+        want, s, nocc, _ = oracle.snow_channel(pts, table, DIV, fd[5], fs[5], mi[5], mx[5], theta=theta)
+        assert nocc.max() >= n_col * 0.6, 'test set-up: most flakes of the column must claim a piece of the first beams'
+        tid = engine.upload_tables([table] * 64)
+        r = run_full(engine, tid, pts, list(range(64)), theta=theta)
+        engine.free_tables(tid)
+        assert np.array_equal(r['full'], want), f'{n_col} flakes'
+        assert np.array_equal(r['nocc'], nocc)
+        assert np.isclose(r['stats'][0, 3], s, rtol=1e-12, atol=0)
+
+
+def test_more_than_128_occluders_is_an_error(engine):
+    """The engine's only hard cap (LSS_ERR_OCCLUDER_OVERFLOW, no reference analogue: the reference's lists are unbounded;
+    the surveyed densities give at most 14-28 occluders per beam)."""
+    table = _column_of_flakes(400, 23)
+    pts = np.array([[50.0, 0.0, 0.0, 90.0, 5.0], [0.0, 30.0, 0.0, 80.0, 5.0]], dtype=np.float32)
+    tid = engine.upload_tables([table] * 64)
+    d_pc = torch.from_numpy(pts).cuda()
+    engine.snowfall_batch(tid, d_pc, np.array([0, 2], dtype=np.int64), np.arange(64, dtype=np.int32)[None], DIV,
+                          threshold_filter=False)
+    with pytest.raises(RuntimeError, match='occluders'):
+        engine.check()
+    engine.free_tables(tid)
+    engine.check()                                         # the latched status is cleared by the failing check
+
+
+def test_augment_snowfall_rate_signature(engine, tmp_path, monkeypatch):
+    """The north-star call shape augment_snowfall(pc, snowfall_rate, terminal_velocity, mode): prefix derived like the
+    reference's callers do (precompute.py:57-58,101), tables sampled once, written under the reference's file names
+    and found there by plain augment() afterwards."""
+    from lidar_snow_sim_b200.snowfall import simulation as sim
+    from lidar_snow_sim_b200.snowfall.sampling import particle_file_prefix, sample_table_set
+    monkeypatch.setenv('LSS_NPY_DIR', str(tmp_path))
+    pc = synthetic_cloud(seed=9, n_azimuth=256)
+    order = np.random.default_rng(3).permutation(64).tolist()
+    poly = np.array([1e-3, -0.2, 14.0])
+    s1, a1 = sim.augment_snowfall(pc, 2.5, 1.6, 'gunn', only_camera_fov=False, engine=engine, write_tables=True,
+                                  order=order, thresh_poly=poly)
+    prefix = particle_file_prefix('gunn', 2.5, 1.6)
+    assert sorted(p.name for p in tmp_path.iterdir()) == sorted(f'{prefix}_{k}.npy' for k in range(1, 65))
+    s2, a2 = sim.augment(pc, prefix, DIV, only_camera_fov=False, engine=engine, order=order, thresh_poly=poly)
+    s3, a3 = sim.augment(pc, 'unused', DIV, only_camera_fov=False, engine=engine, order=order, thresh_poly=poly,
+                         tables=sample_table_set('gunn', 2.5, 1.6, seed=1000))
+    assert s1 == s2 == s3 and np.array_equal(a1, a2) and np.array_equal(a1, a3) and a1.shape[0] > 0
+    with pytest.raises(FileNotFoundError):
+        sim.augment(pc, 'gunn_1.0_2.0', DIV, engine=engine)
