@@ -37,6 +37,9 @@ def needs_build():
 
 def build(force=False, verbose=False, extra=()):
     """Compile every translation unit (in parallel, objects under csrc/_obj/) and link the shared library."""
+    env_extra = os.environ.get('LSS_NVCC_FLAGS', '').split()       # tuning experiments: e.g. -DLSS_SOLVE_CTAS=5
+    if env_extra:
+        extra, force = list(extra) + env_extra, True
     if not force and not needs_build():
         return LIB
     from concurrent.futures import ThreadPoolExecutor

@@ -74,8 +74,6 @@ lss_status lss_create(int device, lss_engine **out)
     int zero = 0;
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (e->n_sm <= 0) e->n_sm = 148;
-    const char *old = getenv("LSS_OLD_SOLVE");
-    e->old_solve = old && old[0] == '1';
     if (cudaMalloc(&e->d_R, sizeof(R)) != cudaSuccess || cudaMalloc(&e->d_status, sizeof(int)) != cudaSuccess ||
         cudaMalloc(&e->d_wtab, sizeof(double) * wtab.size()) != cudaSuccess ||
         cudaMemcpy(e->d_wtab, wtab.data(), sizeof(double) * wtab.size(), cudaMemcpyHostToDevice) != cudaSuccess ||

@@ -3,6 +3,17 @@
 #pragma once
 #include "common.cuh"
 
+// One beam of the solve list, written by the scan kernel (32 bytes).  The scan has already walked the beam's whole
+// bucket prefix, so it hands over which prefix positions hit (first 64 positions as a bit mask) and the azimuth.
+struct __align__(16) SolveItem {
+    unsigned long long key;       // work class << 48 | cloud << 32 | row
+    unsigned long long mask;      // bit t: prefix entry e0 + t intersects the beam (t < 64)
+    int e0;                       // first entry of the beam's azimuth bucket
+    int plen_L;                   // prefix length (entries nearer than the target, capped at 65535) << 16 | occluders (capped)
+    float th32;                   // beam azimuth in [0, 2 pi) as the scan used it
+    int bucket;                   // azimuth bucket
+};
+
 // argument block of the per-beam kernels (global type: it crosses translation units)
 struct DevArgs {
     // tables
@@ -45,6 +56,11 @@ struct DevArgs {
     unsigned long long *list_out;
     int *count_out;
     int cap_out;
+    // solve list (scan kernel -> sort -> solve kernel); hdr = the list header ints (LIST_HDR_BYTES)
+    SolveItem *items_out;
+    const SolveItem *items_in;
+    int *hdr;
+    int items_cap;
 };
 
 namespace {
@@ -112,4 +128,5 @@ __device__ __noinline__ float azimuth32(float y, float x)
 
 // solve.cu: the dense solve kernel over the (sorted) solve list; beams it cannot take (more than SOLVE_LCAP occluders or
 // a bucket prefix longer than it tracks) go to list_out for the overflow kernel.  hdr[2] is its tile cursor (zeroed).
+void lss_launch_scan(const DevArgs &a, int64_t max_rows, int n_clouds, cudaStream_t stream);
 void lss_launch_solve(const DevArgs &a, int *tile_cursor, int n_sm, cudaStream_t stream);

@@ -69,7 +69,6 @@ struct lss_engine {
     double *d_R = nullptr;              // range grid, LSS_M_EXT doubles
     double2 *d_wtab = nullptr;          // (sin, cos)(pi R[k] / (c tau)), LSS_M_EXT entries (solve.cu)
     int n_sm = 148;                     // multiprocessors of the device (persistent grids)
-    bool old_solve = false;             // LSS_OLD_SOLVE=1: round-1 solve kernel (A/B measurements)
     int *d_status = nullptr;            // latched asynchronous device status
     std::map<int, TableSet> tables;
     int next_table_id = 1;

@@ -497,8 +497,7 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
 // [2 * LIST_CLASSES + c] class cursors.  Order inside a class is arbitrary: the results do not depend on list order.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int SORT_PER_THREAD = 8;
-__global__ void __launch_bounds__(256) k_list_sort(const unsigned long long *__restrict__ in, unsigned long long *out,
-                                                    int *hdr, int cap)
+__global__ void __launch_bounds__(256) k_list_sort(const SolveItem *__restrict__ in, SolveItem *out, int *hdr, int cap)
 {
     __shared__ int base[LIST_CLASSES], hist[LIST_CLASSES], blk[LIST_CLASSES];
     const int cnt = min(hdr[0], cap);
@@ -523,14 +522,13 @@ __global__ void __launch_bounds__(256) k_list_sort(const unsigned long long *__r
     // rank inside the block (shared-memory counters, warp-aggregated), then ONE global cursor update per class and
     // block: the neighbouring beams of a cloud fall into few classes, per-entry global atomics would serialise
     const int lane = threadIdx.x & 31;
-    unsigned long long it[SORT_PER_THREAD];
-    int rank[SORT_PER_THREAD];
+    int cls_of[SORT_PER_THREAD], rank[SORT_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < SORT_PER_THREAD; k++) {
         const int slot = first + k * 256 + threadIdx.x;
         const bool on = slot < cnt;
-        it[k] = on ? in[slot] : ~0ull;
-        const int cls = on ? (int)(it[k] >> 48) : -1;
+        const int cls = on ? (int)(in[slot].key >> 48) : -1;
+        cls_of[k] = cls;
         const unsigned m = __match_any_sync(0xffffffffu, cls);
         const int leader = __ffs(m) - 1;
         int r = 0;
@@ -544,9 +542,12 @@ __global__ void __launch_bounds__(256) k_list_sort(const unsigned long long *__r
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < SORT_PER_THREAD; k++)
-        if (it[k] != ~0ull) {
-            const int cls = (int)(it[k] >> 48);
-            out[base[cls] + blk[cls] + rank[k]] = it[k];
+        if (cls_of[k] >= 0) {
+            const int slot = first + k * 256 + threadIdx.x;
+            const uint4 *src = reinterpret_cast<const uint4 *>(in + slot);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + base[cls_of[k]] + blk[cls_of[k]] + rank[k]);
+            dst[0] = src[0];
+            dst[1] = src[1];
         }
 }
 
@@ -749,8 +750,8 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     // counters: int[B*2] | unsigned att_cnt[B*64] | unsigned long long att_sum[B]
     w.counters_bytes = align_up((int64_t)n_clouds * 2 * 4, 8) + (int64_t)n_clouds * LSS_N_CHANNELS * 4 + (int64_t)n_clouds * 8;
     w.counters = o;   o = align_up(o + w.counters_bytes, 256);
-    // counts (padded) | overflow list | solve list (every beam may have occluders)
-    w.ovf = o;        o = align_up(o + LIST_HDR_BYTES + (int64_t)OVF_LIST_CAP * 8 + 2 * n_total * 8, 256);
+    // list header | overflow list | solve list, unsorted + sorted (every beam may have occluders)
+    w.ovf = o;        o = align_up(o + LIST_HDR_BYTES + (int64_t)OVF_LIST_CAP * 8 + 2 * n_total * (int64_t)sizeof(SolveItem), 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -887,30 +888,30 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     a.att_sum = d_att_sum;
     a.status = e->d_status;
     unsigned long long *d_ovf_list = (unsigned long long *)(ws + w.ovf + LIST_HDR_BYTES);
-    unsigned long long *d_solve_list = d_ovf_list + OVF_LIST_CAP;
-    unsigned long long *d_sorted_list = d_solve_list + N;
+    SolveItem *d_solve_list = (SolveItem *)(d_ovf_list + OVF_LIST_CAP);
+    SolveItem *d_sorted_list = d_solve_list + N;
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
-        // 1. scan: all beams; the ones without occluders are finished, the others go to the solve list
+        const int items_cap = (int)std::min<int64_t>(N, 0x7fffffff);
+        // 1. scan: all beams; the ones without occluders are finished, the others go to the solve list with their hit masks
         a.list_in = nullptr; a.count_in = nullptr; a.cap_in = 0;
-        a.list_out = d_solve_list; a.count_out = d_counts2; a.cap_out = (int)std::min<int64_t>(N, 0x7fffffff);
-        dim3 grid((unsigned)((max_n + SNOW_TPB - 1) / SNOW_TPB), B);
+        a.list_out = nullptr; a.count_out = nullptr; a.cap_out = 0;
+        a.hdr = d_counts2;
+        a.items_out = d_solve_list; a.items_in = nullptr; a.items_cap = items_cap;
         {
             KernelTimer ks(e, LSS_K_SCAN, stream);
-            k_snowfall<FAST_CAP, MODE_SCAN><<<grid, SNOW_TPB, 0, stream>>>(a);
+            lss_launch_scan(a, max_n, B, stream);
         }
-        // 2. solve: the listed beams, densely packed (every lane has occluders); CTAs beyond the list exit at once
-        k_list_sort<<<(unsigned)((N + 256 * SORT_PER_THREAD - 1) / (256 * SORT_PER_THREAD)), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, a.cap_out);
-        a.list_in = d_sorted_list; a.count_in = d_counts2; a.cap_in = a.cap_out;
+        // 2. solve: the listed beams, sorted by work class, one warp per tile of 32 (persistent grid)
+        k_list_sort<<<(unsigned)((N + 256 * SORT_PER_THREAD - 1) / (256 * SORT_PER_THREAD)), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, items_cap);
+        a.items_in = d_sorted_list; a.items_out = nullptr;
+        a.count_in = d_counts2; a.cap_in = items_cap;
         a.list_out = d_ovf_list; a.count_out = d_counts2 + 1; a.cap_out = OVF_LIST_CAP;
         {
             KernelTimer ks(e, LSS_K_SOLVE, stream);
-            if (e->old_solve)        // round-1 list kernel (A/B measurements: LSS_OLD_SOLVE=1)
-                k_snowfall<FAST_CAP, MODE_LIST><<<(unsigned)((N + SNOW_TPB - 1) / SNOW_TPB), SNOW_TPB, 0, stream>>>(a);
-            else
-                lss_launch_solve(a, d_counts2 + 2, e->n_sm, stream);
+            lss_launch_solve(a, d_counts2 + 2, e->n_sm, stream);
         }
-        // 3. overflow: beams with more than FAST_CAP occluders (rare), redone with SLOW_CAP
+        // 3. overflow: beams with more occluders than the solve kernel's arena takes per beam (rare), round-1 list kernel
         a.list_in = d_ovf_list; a.count_in = d_counts2 + 1; a.cap_in = OVF_LIST_CAP;
         a.list_out = nullptr; a.count_out = nullptr; a.cap_out = 0;
         k_snowfall<SLOW_CAP, MODE_LIST><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);

@@ -1,15 +1,24 @@
-// solve.cu -- the dense solve kernel: every beam of the (work-class sorted) solve list has at least one occluder.
+// solve.cu -- the two per-beam kernels of the snowfall path.
 //
-// Replaces, per listed beam, get_occlusions + compute_occlusion_dict + the waveform loop of process_single_channel
-// (tools/snowfall/simulation.py:118-188, 231-424).  Design (round 2; the round-1 kernel kept per-thread lists in local
-// memory -- 180 MB of it across the resident threads, thrashing L2 -- published one descriptor per waveform sample
+//   k_scan   every beam of the batch, one thread per beam, rows in INPUT order: float32 range / azimuth, walk of the
+//            beam's azimuth bucket of its channel's snowflake plane (float32 broad phase, exact float64 disk / wedge test)
+//            over the WHOLE prefix of entries nearer than the target.  Beams without occluder (~2/3) are finished here;
+//            the others are pushed to the solve list together with what the walk found: the bit mask of the prefix
+//            positions that hit, the bucket, the azimuth.                    (tools/snowfall/simulation.py:80-101, 329-390)
+//   k_solve  the listed beams, sorted by work class: tangent angles of the hits, nearest-first claiming of the beam's
+//            angular sub-intervals, summed sin^2 waveform + argmax, relabel / move the point, label-1 statistics.
+//                                                                              (simulation.py:118-188, 231-295, 391-424)
+//
+// Design of k_solve (round 2; the round-1 kernel kept per-thread lists in local memory -- 180 MB of it across the
+// resident threads, thrashing L2 --, walked the bucket a second time, published one descriptor per waveform sample
 // lane-serially and evaluated a float64 sinpi per sample and pulse):
-//
 //   * persistent grid, one warp = one tile of 32 listed beams, tiles handed out by an atomic cursor (the list is sorted
 //     costliest class first, so the tail is cheap tiles);
 //   * NO local memory: the beams of a warp share a shared-memory arena of ARENA slots, allocated exactly
-//     (occluders + 1 per beam) with a warp scan after a counting pass over the beam's bucket prefix; the counting pass
-//     leaves a 64-bit hit mask, so the fill pass only touches the hits again;
+//     (occluders + 1 per beam) with a warp scan of the counts the scan kernel delivered;
+//   * the hits are loaded COOPERATIVELY: arena slot s is filled by lane s mod 32, whatever beam it belongs to (owner by
+//     a shuffle binary search over the offsets, the slot's prefix position = the r-th set bit of the owner's mask), so
+//     the dependent entry -> record loads of all beams are in flight together; the owner then orders its few slots by range;
 //   * nearest-first claiming runs in place in the arena: the union list lives in the slots of the already processed
 //     hits, pulses (range, ratio) are compacted to the front;
 //   * waveform: sin(pi (R_k - r) / (c tau)) = sin(pi a_k) cos(pi b) - cos(pi a_k) sin(pi b) with a_k = R_k / (c tau) from a
@@ -17,8 +26,8 @@
 //     sample costs a 16-byte load and six float64 operations instead of a sinpi;
 //   * an isolated pulse is unimodal: its owner evaluates the three samples around the peak itself; groups of
 //     overlapping pulses are summed over their whole union window (in dict order, like the reference's i[k] +=) by ALL 32
-//     lanes of the warp, one group at a time, and reduced with three integer warp reductions (first maximum wins,
-//     np.argmax).
+//     lanes of the warp, one group at a time, 128 samples per pass in four register accumulators per lane, and reduced
+//     with three integer warp reductions (first maximum wins, np.argmax).
 //
 // Beams the arena cannot take (more than SOLVE_LCAP occluders) go to the overflow list and are redone by the
 // round-1 list kernel (snowfall.cu, k_snowfall<SLOW_CAP, MODE_LIST>), which has no such limit below 128.
@@ -28,8 +37,14 @@ namespace {
 
 constexpr int SOLVE_TPB = 128;
 constexpr int SOLVE_WARPS = SOLVE_TPB / 32;
-constexpr int SOLVE_CTAS_PER_SM = 6;
-constexpr int ARENA = 256;                 // slots per warp: sum over the 32 beams of (occluders + 1); more -> extra round
+#ifndef LSS_SOLVE_CTAS
+#define LSS_SOLVE_CTAS 6
+#endif
+#ifndef LSS_SOLVE_ARENA
+#define LSS_SOLVE_ARENA 256
+#endif
+constexpr int SOLVE_CTAS_PER_SM = LSS_SOLVE_CTAS;
+constexpr int ARENA = LSS_SOLVE_ARENA;                 // slots per warp: sum over the 32 beams of (occluders + 1); more -> extra round
 constexpr int SOLVE_LCAP = 63;             // occluders per beam handled here (needs LCAP + 1 <= ARENA)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -37,6 +52,18 @@ struct Beam {                              // what the narrow phase needs of a b
     double d, right, left;
     bool straddle;
 };
+
+// beam limits of simulation.py:91-101 from the float32 azimuth (already shifted into [0, 2 pi))
+__device__ __forceinline__ void beam_limits(float th32, double half_div, Beam &bm)
+{
+    const double thd = (double)th32;
+    double right = thd - half_div, left = thd + half_div;
+    if (right < 0) right += LSS_TWO_PI;
+    if (left < 0) left += LSS_TWO_PI;
+    if (right > LSS_TWO_PI) right -= LSS_TWO_PI;
+    if (left > LSS_TWO_PI) left -= LSS_TWO_PI;
+    bm.right = right; bm.left = left; bm.straddle = right > left;
+}
 
 // simulation.py:345-385 for one particle: planar range strictly below the target range, centre inside the beam or
 // disk crossing one of the two limit rays
@@ -53,6 +80,123 @@ __device__ __forceinline__ bool exact_hit(const ParticleRec *rp, const Beam &bm,
     return inside || right_hit || left_hit;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// scan: all beams
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
+{
+    __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y, blk0 = blockIdx.x * SNOW_TPB, i = blk0 + threadIdx.x;
+    const int64_t beg = a.cloud_off[b];
+    const int n = (int)(a.cloud_off[b + 1] - beg);
+    if (blk0 >= n) return;
+    const bool active = i < n;
+    const int w0 = blk0 + 32 * wid;                                 // first row of this warp
+    const int nf_w = max(0, min(32, n - w0)) * 5;                   // floats of this warp's rows
+    float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
+    {   // coalesced load of the warp's 32 rows (160 floats); no block-wide barrier anywhere in this kernel
+        const float *src = a.pts + (beg + w0) * 5;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int f = q * 32 + lane;
+            if (f < nf_w) s_rows[wid][f] = __ldcs(src + f);         // streamed once: do not displace the table index in L2
+        }
+        __syncwarp();
+        if (active) {
+            const float *row = &s_rows[wid][5 * lane];
+            px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
+        }
+    }
+    // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
+    const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+    const int ch = channel_bin(pch);
+    float out_l = pch;
+    int L = 0, plen = 0, e0 = 0, bk = 0;
+    unsigned long long mask = 0ull;
+    float th32 = 0.0f;
+    if (active && ch < LSS_N_CHANNELS) {
+        out_l = 0.0f;
+        th32 = a.theta ? a.theta[beg + i] : azimuth32(py, px);
+        if (th32 < 0.0f) th32 = __fadd_rn(th32, 6.2831855f);
+        Beam bm;
+        bm.d = (double)d32;
+        beam_limits(th32, a.half_div, bm);
+        const double thd = (double)th32;
+        const int plane = a.order[b * LSS_N_CHANNELS + ch];
+        if (plane >= 0 && plane < a.n_planes && thd == thd) {
+            const double thm = thd >= LSS_TWO_PI ? thd - LSS_TWO_PI : thd;
+            bk = (int)(thm * a.inv_w);
+            bk = bk < 0 ? 0 : (bk >= a.n_buckets ? a.n_buckets - 1 : bk);
+            const float th_rel = (float)(thm - (bk + 0.5) * a.w);
+            const int32_t *bs = a.bucket_start + (int64_t)plane * (a.n_buckets + 1) + bk;
+            e0 = bs[0];
+            const int e1 = bs[1];
+            int e = e0;
+#pragma unroll 1
+            for (; e < e1; e++) {
+                const BroadEntry en = __ldg(&a.entries[e]);
+                if (!(en.x < d32)) break;                           // sorted by range: nothing nearer follows
+                if (!(fabsf(en.y - th_rel) <= en.z)) continue;       // float32 broad phase (conservative)
+                double rho;
+                bool rh, lh;
+                if (!exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) continue;
+                const int t = e - e0;
+                if (t < 64) mask |= 1ull << t;
+                L++;
+            }
+            plen = e - e0;
+        }
+    }
+    // ---- beams with occluders: warp-aggregated push to the solve list ---------------------------------------------------
+    {
+        const bool push = L > 0;
+        const unsigned pm = __ballot_sync(FULL, push);
+        if (push) {
+            int base = 0;
+            const int leader = __ffs(pm) - 1;
+            if (lane == leader) base = atomicAdd(a.hdr, __popc(pm));
+            base = __shfl_sync(pm, base, leader);
+            // work class: everything a beam costs the solve kernel (occluders, samples) grows with the target range; the
+            // costliest class comes first so that the kernel's tail is cheap tiles
+            const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
+            const int slot = base + __popc(pm & ((1u << lane) - 1u));
+            if (slot < a.items_cap) {
+                SolveItem it;
+                it.key = ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
+                it.mask = mask;
+                it.e0 = e0;
+                it.plen_L = (min(plen, 65535) << 16) | min(L, 65535);
+                it.th32 = th32;
+                it.bucket = bk;
+                a.items_out[slot] = it;
+            }
+            const unsigned cm = __match_any_sync(pm, cls);
+            if (lane == __ffs(cm) - 1) atomicAdd(a.hdr + LIST_CLASSES + cls, __popc(cm));
+        }
+    }
+    // ---- rows back through shared memory (coalesced store); the listed beams' rows are rewritten by the solve kernel ------
+    __syncwarp();
+    if (active) {
+        float *row = &s_rows[wid][5 * lane];
+        row[3] = rintf(pint);                                       // np.round of the intensity column (simulation.py:516)
+        row[4] = out_l;
+        if (a.nocc) a.nocc[beg + i] = 0;
+    }
+    __syncwarp();
+    {
+        float *dst = a.aug + (beg + w0) * 5;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const int f = q * 32 + lane;
+            if (f < nf_w) dst[f] = s_rows[wid][f];                  // read back by k_keep / k_scatter from L2
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// solve: the listed beams
+// ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pack_win(int ks, int ke, int k0)
 {
     return (unsigned long long)(unsigned)ks | ((unsigned long long)(unsigned)ke << 11) | ((unsigned long long)(unsigned)k0 << 22);
@@ -70,6 +214,13 @@ __device__ __forceinline__ void pulse_phase(double r, double &sb, double &cb)
     const double corr = LSS_PI * bl;
     sb = fma(corr, c, s);
     cb = fma(-corr, s, c);
+}
+
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    const long long b = __double_as_longlong(v);
+    const int lo = __shfl_sync(FULL, (int)(unsigned)b, src), hi = __shfl_sync(FULL, (int)(b >> 32), src);
+    return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
 __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs a, int *tile_cursor)
@@ -94,9 +245,11 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         if (tile >= n_tiles) break;
         const int slot = tile * 32 + lane;
         const bool active = slot < cnt;
-        const unsigned long long it = active ? a.list_in[slot] : 0ull;
-        const int b = (int)((it >> 32) & 0xffffu);
-        const int i = (int)(it & 0xffffffffu);
+        SolveItem it;
+        it.key = 0ull; it.mask = 0ull; it.e0 = 0; it.plen_L = 0; it.th32 = 0.0f; it.bucket = 0;
+        if (active) it = a.items_in[slot];
+        const int b = (int)((it.key >> 32) & 0xffffu);
+        const int i = (int)(it.key & 0xffffffffu);
         const int64_t beg = a.cloud_off[b];
         float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
         if (active) {
@@ -106,62 +259,27 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
         const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
         const int ch = channel_bin(pch);
-        const bool valid = active && ch < LSS_N_CHANNELS;
 
-        float out_x = px, out_y = py, out_z = pz, out_i = pint, out_l = valid ? 0.0f : pch;
+        float out_x = px, out_y = py, out_z = pz, out_i = pint, out_l = active ? 0.0f : pch;
         long long att_new_i = -1;
         int n_claim = 0;
 
-        // ---- beam limits (simulation.py:91-101) and the counting pass over the beam's azimuth bucket -------------------
+        // what the scan kernel found on this beam's bucket prefix
+        const int L = active ? (it.plen_L & 0xffff) : 0;
+        const int plen = it.plen_L >> 16 & 0xffff;
+        const unsigned mask_lo = (unsigned)it.mask, mask_hi = (unsigned)(it.mask >> 32);
+        const int n_masked = __popc(mask_lo) + __popc(mask_hi);     // hits among the first 64 prefix positions
         Beam bm;
         bm.d = (double)d32;
-        bm.right = bm.left = 0.0;
-        bm.straddle = false;
-        int e0 = 0, plen = 0, L = 0;
-        unsigned long long mask = 0ull;
-        float th_rel = 0.0f;
-        if (valid) {
-            float th32 = a.theta ? a.theta[beg + i] : azimuth32(py, px);
-            if (th32 < 0.0f) th32 = __fadd_rn(th32, 6.2831855f);
-            const double thd = (double)th32;
-            double right = thd - a.half_div, left = thd + a.half_div;
-            if (right < 0) right += LSS_TWO_PI;
-            if (left < 0) left += LSS_TWO_PI;
-            if (right > LSS_TWO_PI) right -= LSS_TWO_PI;
-            if (left > LSS_TWO_PI) left -= LSS_TWO_PI;
-            bm.right = right; bm.left = left; bm.straddle = right > left;
-            const int plane = a.order[b * LSS_N_CHANNELS + ch];
-            if (plane >= 0 && plane < a.n_planes && thd == thd) {
-                const double thm = thd >= LSS_TWO_PI ? thd - LSS_TWO_PI : thd;
-                int bk = (int)(thm * a.inv_w);
-                bk = bk < 0 ? 0 : (bk >= a.n_buckets ? a.n_buckets - 1 : bk);
-                th_rel = (float)(thm - (bk + 0.5) * a.w);
-                const int32_t *bs = a.bucket_start + (int64_t)plane * (a.n_buckets + 1) + bk;
-                e0 = bs[0];
-                const int e1 = bs[1];
-                int e = e0;
-#pragma unroll 1
-                for (; e < e1; e++) {
-                    const BroadEntry en = __ldg(&a.entries[e]);
-                    if (!(en.x < d32)) break;                       // sorted by range: nothing nearer follows
-                    if (!(fabsf(en.y - th_rel) <= en.z)) continue;   // float32 broad phase (conservative)
-                    double rho;
-                    bool rh, lh;
-                    if (!exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) continue;
-                    const int t = e - e0;
-                    if (t < 64) mask |= 1ull << t;
-                    L++;
-                }
-                plen = e - e0;
-            }
-        }
-        const bool deferred = L > SOLVE_LCAP;
+        beam_limits(it.th32, a.half_div, bm);
+
+        const bool deferred = L > SOLVE_LCAP || (L > n_masked && plen >= 65535);
         if (deferred) {
             const int s2 = atomicAdd(a.count_out, 1);
             if (s2 < a.cap_out) a.list_out[s2] = ((unsigned long long)b << 32) | (unsigned)i;
             else raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
         }
-        const int need = (valid && L > 0 && !deferred) ? L + 1 : 0;
+        const int need = (L > 0 && !deferred) ? L + 1 : 0;
 
         // ---- rounds: as many beams of the tile as fit into the arena (normally all of them) ---------------------------
         unsigned remaining = __ballot_sync(FULL, need > 0);
@@ -176,44 +294,80 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             }
             const bool in_round = rem && incl <= ARENA;
             remaining &= ~__ballot_sync(FULL, in_round);
-            const int off = incl - mine;
+            const int off = incl - mine;                            // exclusive offsets: non-decreasing over the lanes
+            const int total = (int)__reduce_max_sync(FULL, in_round ? (unsigned)incl : 0u);
             int n_pulses = 0;
             double best = 0.0;
             int kbest = 0;
 
-            if (in_round) {
-                // ---- fill pass: (a1, a2, range) of every hit, inserted by range (np.argsort, simulation.py:416) -------
-                int nh = 0;
-                auto add_hit = [&](const ParticleRec *rp, double rho, bool right_hit, bool left_hit) {
-                    const double a1 = right_hit ? bm.right : rp->t_right;      // geometry.py:26-27
-                    const double a2 = left_hit ? bm.left : rp->t_left;
-                    int j = off + nh - 1;
+            // ---- cooperative fill: arena slot s <- the r-th hit of its owner beam, (a1, a2, range) --------------------
 #pragma unroll 1
-                    while (j >= off && A2[j] > rho) { A0[j + 1] = A0[j]; A1[j + 1] = A1[j]; A2[j + 1] = A2[j]; j--; }
-                    A0[j + 1] = a1; A1[j + 1] = a2; A2[j + 1] = rho;
-                    nh++;
-                };
-                unsigned long long m = mask;
-#pragma unroll 1
-                while (m) {
-                    const int t = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const BroadEntry en = __ldg(&a.entries[e0 + t]);
-                    const ParticleRec *rp = a.rec + __float_as_int(en.w);
-                    double rho;
-                    bool rh, lh;
-                    exact_hit(rp, bm, rho, rh, lh);
-                    add_hit(rp, rho, rh, lh);
+            for (int s0 = 0; s0 < total; s0 += 32) {
+                const int s = s0 + lane;
+                int j = 0;                                          // owner: the last lane whose offset is <= s
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int c = j + step;
+                    const int oc = __shfl_sync(FULL, off, c & 31);
+                    if (c < 32 && oc <= s) j = c;
                 }
-#pragma unroll 1
-                for (int t = 64; t < plen; t++) {                   // long prefixes (dense tables, far targets)
-                    const BroadEntry en = __ldg(&a.entries[e0 + t]);
-                    if (!(fabsf(en.y - th_rel) <= en.z)) continue;
+                const int r = s - __shfl_sync(FULL, off, j);
+                const unsigned lo = __shfl_sync(FULL, mask_lo, j), hi = __shfl_sync(FULL, mask_hi, j);
+                const int e0j = __shfl_sync(FULL, it.e0, j);
+                const int inr = __shfl_sync(FULL, (int)in_round, j);
+                Beam bj;
+                bj.d = shfl_f64(bm.d, j);
+                bj.right = shfl_f64(bm.right, j);
+                bj.left = shfl_f64(bm.left, j);
+                bj.straddle = bj.right > bj.left;
+                const int c0 = __popc(lo);
+                if (s < total && inr && r < c0 + __popc(hi)) {      // (slot L of a beam is its hard target: filled later)
+                    const int t = r < c0 ? (int)__fns(lo, 0, r + 1) : 32 + (int)__fns(hi, 0, r + 1 - c0);
+                    const BroadEntry en = __ldg(&a.entries[e0j + t]);
                     const ParticleRec *rp = a.rec + __float_as_int(en.w);
                     double rho;
                     bool rh, lh;
-                    if (!exact_hit(rp, bm, rho, rh, lh)) continue;
-                    add_hit(rp, rho, rh, lh);
+                    exact_hit(rp, bj, rho, rh, lh);
+                    A0[s] = rh ? bj.right : rp->t_right;            // geometry.py:26-27
+                    A1[s] = lh ? bj.left : rp->t_left;
+                    A2[s] = rho;
+                }
+            }
+            __syncwarp();
+
+            if (in_round) {
+                int nh = n_masked;
+                if (L > n_masked) {                                 // long prefixes (dense tables, far targets): positions >= 64
+                    const double thd = (double)it.th32;
+                    const double thm = thd >= LSS_TWO_PI ? thd - LSS_TWO_PI : thd;
+                    const float th_rel = (float)(thm - (it.bucket + 0.5) * a.w);
+#pragma unroll 1
+                    for (int t = 64; t < plen; t++) {
+                        const BroadEntry en = __ldg(&a.entries[it.e0 + t]);
+                        if (!(fabsf(en.y - th_rel) <= en.z)) continue;
+                        const ParticleRec *rp = a.rec + __float_as_int(en.w);
+                        double rho;
+                        bool rh, lh;
+                        if (!exact_hit(rp, bm, rho, rh, lh)) continue;
+                        if (nh < L) {
+                            A0[off + nh] = rh ? bm.right : rp->t_right;
+                            A1[off + nh] = lh ? bm.left : rp->t_left;
+                            A2[off + nh] = rho;
+                        }
+                        nh++;
+                    }
+                }
+                // order by range (np.argsort, simulation.py:416); the prefix is sorted by the float32 range already, so this
+                // insertion sort almost never moves anything; equal ranges keep their prefix order
+#pragma unroll 1
+                for (int p = 1; p < L; p++) {
+                    const double rho = A2[off + p];
+                    if (!(A2[off + p - 1] > rho)) continue;
+                    const double a1 = A0[off + p], a2 = A1[off + p];
+                    int q = p - 1;
+#pragma unroll 1
+                    while (q >= 0 && A2[off + q] > rho) { A0[off + q + 1] = A0[off + q]; A1[off + q + 1] = A1[off + q]; A2[off + q + 1] = A2[off + q]; q--; }
+                    A0[off + q + 1] = a1; A1[off + q + 1] = a2; A2[off + q + 1] = rho;
                 }
 
                 // ---- compute_occlusion_dict (simulation.py:231-295) ------------------------------------------------------
@@ -358,28 +512,51 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                     double gb = 0.0;
                     unsigned gk = 0u;
 #pragma unroll 1
-                    for (int base = klo; base < khi; base += 32) {
-                        const int k = base + lane;
-                        const bool on = k < khi;
-                        double v = 0.0;
-                        if (on) {
-                            const double2 t = __ldg(&a.wtab[k]);
+                    for (int base = klo; base < khi; base += 128) {
+                        // four samples per lane: k = base + lane + 32 m, accumulators in registers
+                        const int kk = base + lane;
+                        const double2 z = make_double2(0.0, 0.0);
+                        const double2 t0 = kk < khi ? __ldg(&a.wtab[kk]) : z;
+                        const double2 t1 = kk + 32 < khi ? __ldg(&a.wtab[kk + 32]) : z;
+                        const double2 t2 = kk + 64 < khi ? __ldg(&a.wtab[kk + 64]) : z;
+                        const double2 t3 = kk + 96 < khi ? __ldg(&a.wtab[kk + 96]) : z;
+                        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll 1
-                            for (int q = q0; q <= q1; q++) {
-                                const unsigned long long wq = W[q];
-                                if (k >= (int)(wq & 2047u) && k < (int)((wq >> 11) & 2047u)) {
-                                    const double sn = t.x * A3[q] - t.y * A1[q];
-                                    v += A0[q] * (sn * sn);          // pulses in dict order, like the reference's i[k] +=
-                                }
+                        for (int q = q0; q <= q1; q++) {                // pulses in dict order, like the reference's i[k] +=
+                            const unsigned long long wq = W[q];
+                            const int ks = (int)(wq & 2047u), ke = (int)((wq >> 11) & 2047u);
+                            if (ke <= base || ks >= base + 128) continue;   // (uniform over the warp)
+                            const double amp = A0[q], sb = A1[q], cb = A3[q];
+                            if (ks < base + 32 && ke > base && kk >= ks && kk < ke) {
+                                const double sn = t0.x * cb - t0.y * sb;
+                                v0 += amp * (sn * sn);
+                            }
+                            if (ks < base + 64 && ke > base + 32 && kk + 32 >= ks && kk + 32 < ke) {
+                                const double sn = t1.x * cb - t1.y * sb;
+                                v1 += amp * (sn * sn);
+                            }
+                            if (ks < base + 96 && ke > base + 64 && kk + 64 >= ks && kk + 64 < ke) {
+                                const double sn = t2.x * cb - t2.y * sb;
+                                v2 += amp * (sn * sn);
+                            }
+                            if (ke > base + 96 && kk + 96 >= ks && kk + 96 < ke) {
+                                const double sn = t3.x * cb - t3.y * sb;
+                                v3 += amp * (sn * sn);
                             }
                         }
-                        // warp argmax (non-negative doubles order like their bit patterns): max high word, max low word
-                        // among those, min sample index among the exact ties -> the first maximum, like np.argmax
+                        // this lane's first maximum (ascending sample index), then the warp's: non-negative doubles order
+                        // like their bit patterns -> max high word, max low word among those, min sample index among the
+                        // exact ties = the first maximum, like np.argmax
+                        double v = v0;
+                        int k = kk;
+                        if (v1 > v) { v = v1; k = kk + 32; }
+                        if (v2 > v) { v = v2; k = kk + 64; }
+                        if (v3 > v) { v = v3; k = kk + 96; }
                         const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
                         const unsigned vhi = (unsigned)(vb >> 32), vlo = (unsigned)vb;
                         const unsigned mhi = __reduce_max_sync(FULL, vhi);
                         const unsigned mlo = __reduce_max_sync(FULL, vhi == mhi ? vlo : 0u);
-                        const bool is_max = on && (vhi == mhi) && (vlo == mlo);
+                        const bool is_max = (vhi == mhi) && (vlo == mlo);
                         const unsigned kmin = __reduce_min_sync(FULL, is_max ? (unsigned)k : 0xffffffffu);
                         const double vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
                         if (vmax > gb) { gb = vmax; gk = kmin; }      // ascending windows: the earlier sample keeps a tie
@@ -437,6 +614,12 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
 }
 
 }  // namespace
+
+void lss_launch_scan(const DevArgs &a, int64_t max_rows, int n_clouds, cudaStream_t stream)
+{
+    const dim3 grid((unsigned)((max_rows + SNOW_TPB - 1) / SNOW_TPB), (unsigned)n_clouds);
+    k_scan<<<grid, SNOW_TPB, 0, stream>>>(a);
+}
 
 void lss_launch_solve(const DevArgs &a, int *tile_cursor, int n_sm, cudaStream_t stream)
 {
