@@ -4,14 +4,15 @@
 #include "common.cuh"
 
 // One beam of the solve list, written by the scan kernel (32 bytes).  The scan has already walked the beam's whole
-// bucket prefix, so it hands over which prefix positions hit (first 64 positions as a bit mask) and the azimuth.
+// bucket prefix and tested every candidate exactly, so it hands over WHICH prefix entries hit (their positions, in
+// prefix order, in the hit-position array) and the azimuth it used.
 struct __align__(16) SolveItem {
     unsigned long long key;       // work class << 48 | cloud << 32 | row
-    unsigned long long mask;      // bit t: prefix entry e0 + t intersects the beam (t < 64)
     int e0;                       // first entry of the beam's azimuth bucket
-    int plen_L;                   // prefix length (entries nearer than the target, capped at 65535) << 16 | occluders (capped)
+    int hit_off;                  // first of the beam's L positions in hit_pos[]
+    int L;                        // occluders
     float th32;                   // beam azimuth in [0, 2 pi) as the scan used it
-    int bucket;                   // azimuth bucket
+    int pad0, pad1;
 };
 
 // argument block of the per-beam kernels (global type: it crosses translation units)
@@ -59,8 +60,10 @@ struct DevArgs {
     // solve list (scan kernel -> sort -> solve kernel); hdr = the list header ints (LIST_HDR_BYTES)
     SolveItem *items_out;
     const SolveItem *items_in;
-    int *hdr;
+    int *hdr;                    // [0] listed beams, [1] overflow beams, [2] tile cursor, [3] hit positions used, class counts ...
     int items_cap;
+    unsigned short *hit_pos;     // prefix positions of the hits of the listed beams
+    int hit_cap;
 };
 
 namespace {

@@ -83,9 +83,29 @@ __device__ __forceinline__ bool exact_hit(const ParticleRec *rp, const Beam &bm,
 // ---------------------------------------------------------------------------------------------------------------------
 // scan: all beams
 // ---------------------------------------------------------------------------------------------------------------------
+// Two phases per warp (32 consecutive rows), because a thread-per-beam loop that tests a candidate exactly as soon as it
+// finds one pays the latency of that dependent record load in EVERY iteration in which any lane of the warp has a
+// candidate (measured: the exact tests ran at 5 of 32 lanes and dominated the kernel):
+//   A  each lane walks its beam's bucket prefix with the float32 broad phase only -- a streaming read of 16-byte
+//      entries, four loads in flight -- and notes the positions of the survivors (shared memory, SURV_CAP per lane);
+//   B  the survivors of all 32 beams are tested exactly by ALL lanes, one survivor per lane and round (owner by a
+//      shuffle binary search), so the record loads of the whole warp are in flight together; hits are flagged in a
+//      per-beam bit mask.
+// Lanes with more than SURV_CAP survivors (extreme densities) fall back to the serial walk.
+constexpr int SURV_CAP = 20;
+
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    const long long b = __double_as_longlong(v);
+    const int lo = __shfl_sync(FULL, (int)(unsigned)b, src), hi = __shfl_sync(FULL, (int)(b >> 32), src);
+    return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
+}
+
 __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
 {
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
+    __shared__ unsigned short s_pos[SNOW_WARPS][32][SURV_CAP];     // prefix positions of each lane's survivors
+    __shared__ unsigned s_hit[SNOW_WARPS][32];                     // bit r: survivor r of this lane is a hit
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.y, blk0 = blockIdx.x * SNOW_TPB, i = blk0 + threadIdx.x;
     const int64_t beg = a.cloud_off[b];
@@ -94,8 +114,9 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
     const bool active = i < n;
     const int w0 = blk0 + 32 * wid;                                 // first row of this warp
     const int nf_w = max(0, min(32, n - w0)) * 5;                   // floats of this warp's rows
+    if (nf_w <= 0) return;                                          // (whole warps only; no block-wide barrier below)
     float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
-    {   // coalesced load of the warp's 32 rows (160 floats); no block-wide barrier anywhere in this kernel
+    {   // coalesced load of the warp's 32 rows (160 floats)
         const float *src = a.pts + (beg + w0) * 5;
 #pragma unroll
         for (int q = 0; q < 5; q++) {
@@ -112,67 +133,158 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
     const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
     const int ch = channel_bin(pch);
     float out_l = pch;
-    int L = 0, plen = 0, e0 = 0, bk = 0;
-    unsigned long long mask = 0ull;
-    float th32 = 0.0f;
+    int e0 = 0, e1 = 0, ns = 0;
+    bool slow = false;
+    float th32 = 0.0f, th_rel = 0.0f;
+    Beam bm;
+    bm.d = (double)d32; bm.right = bm.left = 0.0; bm.straddle = false;
     if (active && ch < LSS_N_CHANNELS) {
         out_l = 0.0f;
         th32 = a.theta ? a.theta[beg + i] : azimuth32(py, px);
         if (th32 < 0.0f) th32 = __fadd_rn(th32, 6.2831855f);
-        Beam bm;
-        bm.d = (double)d32;
         beam_limits(th32, a.half_div, bm);
         const double thd = (double)th32;
         const int plane = a.order[b * LSS_N_CHANNELS + ch];
         if (plane >= 0 && plane < a.n_planes && thd == thd) {
             const double thm = thd >= LSS_TWO_PI ? thd - LSS_TWO_PI : thd;
-            bk = (int)(thm * a.inv_w);
+            int bk = (int)(thm * a.inv_w);
             bk = bk < 0 ? 0 : (bk >= a.n_buckets ? a.n_buckets - 1 : bk);
-            const float th_rel = (float)(thm - (bk + 0.5) * a.w);
+            th_rel = (float)(thm - (bk + 0.5) * a.w);
             const int32_t *bs = a.bucket_start + (int64_t)plane * (a.n_buckets + 1) + bk;
             e0 = bs[0];
-            const int e1 = bs[1];
-            int e = e0;
+            e1 = bs[1];
+            // ---- phase A: broad phase over the prefix of entries nearer than the target, four loads in flight --------------
+            unsigned short *pos = s_pos[wid][lane];
+            bool stop = false;
 #pragma unroll 1
-            for (; e < e1; e++) {
-                const BroadEntry en = __ldg(&a.entries[e]);
-                if (!(en.x < d32)) break;                           // sorted by range: nothing nearer follows
-                if (!(fabsf(en.y - th_rel) <= en.z)) continue;       // float32 broad phase (conservative)
-                double rho;
-                bool rh, lh;
-                if (!exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) continue;
-                const int t = e - e0;
-                if (t < 64) mask |= 1ull << t;
-                L++;
+            for (int e = e0; e < e1 && !stop; e += 4) {
+                BroadEntry en[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) en[q] = __ldg(&a.entries[min(e + q, e1 - 1)]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (stop || e + q >= e1) continue;
+                    if (!(en[q].x < d32)) { stop = true; continue; }            // sorted by range: nothing nearer follows
+                    if (!(fabsf(en[q].y - th_rel) <= en[q].z)) continue;         // float32 broad phase (conservative)
+                    const int t = e + q - e0;
+                    if (ns < SURV_CAP && t < 65536) pos[ns] = (unsigned short)t;
+                    else slow = true;
+                    ns++;
+                }
             }
-            plen = e - e0;
         }
     }
-    // ---- beams with occluders: warp-aggregated push to the solve list ---------------------------------------------------
+    // ---- phase B: exact tests of the survivors of the whole warp, one per lane and round --------------------------------------
+    s_hit[wid][lane] = 0u;
+    const int mine = slow ? 0 : ns;
+    int incl = mine;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, sft);
+        if (lane >= sft) incl += t;
+    }
+    const int off = incl - mine;
+    const int total = __shfl_sync(FULL, incl, 31);
+    __syncwarp();
+#pragma unroll 1
+    for (int s0 = 0; s0 < total; s0 += 32) {
+        const int s = s0 + lane;
+        int j = 0;                                              // owner: the last lane whose offset is <= s
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const int c = j + step;
+            const int oc = __shfl_sync(FULL, off, c & 31);
+            if (c < 32 && oc <= s) j = c;
+        }
+        const int r = s - __shfl_sync(FULL, off, j);
+        const int e0j = __shfl_sync(FULL, e0, j);
+        Beam bj;
+        bj.d = shfl_f64(bm.d, j);
+        bj.right = shfl_f64(bm.right, j);
+        bj.left = shfl_f64(bm.left, j);
+        bj.straddle = bj.right > bj.left;
+        if (s < total) {
+            const BroadEntry en = __ldg(&a.entries[e0j + s_pos[wid][j][r]]);
+            double rho;
+            bool rh, lh;
+            if (exact_hit(a.rec + __float_as_int(en.w), bj, rho, rh, lh)) atomicOr(&s_hit[wid][j], 1u << r);
+        }
+    }
+    __syncwarp();
+    unsigned hits = s_hit[wid][lane];
+    int L = __popc(hits);
+    if (slow) {                                                 // serial fallback: count the hits of the whole prefix
+        L = 0;
+#pragma unroll 1
+        for (int e = e0; e < e1; e++) {
+            const BroadEntry en = __ldg(&a.entries[e]);
+            if (!(en.x < d32)) break;
+            if (!(fabsf(en.y - th_rel) <= en.z)) continue;
+            double rho;
+            bool rh, lh;
+            if (exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) L++;
+        }
+    }
+    // ---- beams with occluders: warp-aggregated push to the solve list, hit positions to the position array -------------------
     {
         const bool push = L > 0;
         const unsigned pm = __ballot_sync(FULL, push);
-        if (push) {
-            int base = 0;
+        int lincl = push ? L : 0;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int t = __shfl_up_sync(FULL, lincl, sft);
+            if (lane >= sft) lincl += t;
+        }
+        const int ltotal = __shfl_sync(FULL, lincl, 31);
+        if (pm) {
+            int base = 0, hbase = 0;
             const int leader = __ffs(pm) - 1;
-            if (lane == leader) base = atomicAdd(a.hdr, __popc(pm));
-            base = __shfl_sync(pm, base, leader);
-            // work class: everything a beam costs the solve kernel (occluders, samples) grows with the target range; the
-            // costliest class comes first so that the kernel's tail is cheap tiles
-            const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
-            const int slot = base + __popc(pm & ((1u << lane) - 1u));
-            if (slot < a.items_cap) {
-                SolveItem it;
-                it.key = ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
-                it.mask = mask;
-                it.e0 = e0;
-                it.plen_L = (min(plen, 65535) << 16) | min(L, 65535);
-                it.th32 = th32;
-                it.bucket = bk;
-                a.items_out[slot] = it;
+            if (lane == leader) {
+                base = atomicAdd(a.hdr, __popc(pm));
+                hbase = atomicAdd(a.hdr + 3, ltotal);
             }
-            const unsigned cm = __match_any_sync(pm, cls);
-            if (lane == __ffs(cm) - 1) atomicAdd(a.hdr + LIST_CLASSES + cls, __popc(cm));
+            base = __shfl_sync(FULL, base, leader);
+            hbase = __shfl_sync(FULL, hbase, leader);
+            if (push) {
+                // work class: everything a beam costs the solve kernel (occluders, samples) grows with the target range;
+                // the costliest class comes first so that the kernel's tail is cheap tiles
+                const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
+                const int slot = base + __popc(pm & ((1u << lane) - 1u));
+                const int hoff = hbase + lincl - L;
+                const bool fits = hoff + L <= a.hit_cap;
+                if (!fits) raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
+                if (slot < a.items_cap) {
+                    SolveItem it;
+                    it.key = ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
+                    it.e0 = e0;
+                    it.hit_off = hoff;
+                    it.L = fits ? L : 0;
+                    it.th32 = th32;
+                    it.pad0 = 0; it.pad1 = 0;
+                    a.items_out[slot] = it;
+                }
+                if (fits) {
+                    unsigned short *hp = a.hit_pos + hoff;
+                    if (!slow) {
+                        const unsigned short *pos = s_pos[wid][lane];
+#pragma unroll 1
+                        for (int k = 0; hits; hits &= hits - 1) hp[k++] = pos[__ffs(hits) - 1];
+                    } else {
+                        int k = 0;
+#pragma unroll 1
+                        for (int e = e0; e < e1 && k < L; e++) {
+                            const BroadEntry en = __ldg(&a.entries[e]);
+                            if (!(en.x < d32)) break;
+                            if (!(fabsf(en.y - th_rel) <= en.z)) continue;
+                            double rho;
+                            bool rh, lh;
+                            if (exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) hp[k++] = (unsigned short)min(e - e0, 65535);
+                        }
+                    }
+                }
+                const unsigned cm = __match_any_sync(pm, cls);
+                if (lane == __ffs(cm) - 1) atomicAdd(a.hdr + LIST_CLASSES + cls, __popc(cm));
+            }
         }
     }
     // ---- rows back through shared memory (coalesced store); the listed beams' rows are rewritten by the solve kernel ------
@@ -216,13 +328,6 @@ __device__ __forceinline__ void pulse_phase(double r, double &sb, double &cb)
     cb = fma(-corr, s, c);
 }
 
-__device__ __forceinline__ double shfl_f64(double v, int src)
-{
-    const long long b = __double_as_longlong(v);
-    const int lo = __shfl_sync(FULL, (int)(unsigned)b, src), hi = __shfl_sync(FULL, (int)(b >> 32), src);
-    return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
-}
-
 __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs a, int *tile_cursor)
 {
     __shared__ double s_arena[SOLVE_WARPS][4][ARENA];
@@ -246,7 +351,7 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         const int slot = tile * 32 + lane;
         const bool active = slot < cnt;
         SolveItem it;
-        it.key = 0ull; it.mask = 0ull; it.e0 = 0; it.plen_L = 0; it.th32 = 0.0f; it.bucket = 0;
+        it.key = 0ull; it.e0 = 0; it.hit_off = 0; it.L = 0; it.th32 = 0.0f; it.pad0 = it.pad1 = 0;
         if (active) it = a.items_in[slot];
         const int b = (int)((it.key >> 32) & 0xffffu);
         const int i = (int)(it.key & 0xffffffffu);
@@ -264,16 +369,13 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         long long att_new_i = -1;
         int n_claim = 0;
 
-        // what the scan kernel found on this beam's bucket prefix
-        const int L = active ? (it.plen_L & 0xffff) : 0;
-        const int plen = it.plen_L >> 16 & 0xffff;
-        const unsigned mask_lo = (unsigned)it.mask, mask_hi = (unsigned)(it.mask >> 32);
-        const int n_masked = __popc(mask_lo) + __popc(mask_hi);     // hits among the first 64 prefix positions
+        // what the scan kernel found on this beam's bucket prefix: L hits, their prefix positions in hit_pos[hit_off ..]
+        const int L = active ? it.L : 0;
         Beam bm;
         bm.d = (double)d32;
         beam_limits(it.th32, a.half_div, bm);
 
-        const bool deferred = L > SOLVE_LCAP || (L > n_masked && plen >= 65535);
+        const bool deferred = L > SOLVE_LCAP;
         if (deferred) {
             const int s2 = atomicAdd(a.count_out, 1);
             if (s2 < a.cap_out) a.list_out[s2] = ((unsigned long long)b << 32) | (unsigned)i;
@@ -312,7 +414,8 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                     if (c < 32 && oc <= s) j = c;
                 }
                 const int r = s - __shfl_sync(FULL, off, j);
-                const unsigned lo = __shfl_sync(FULL, mask_lo, j), hi = __shfl_sync(FULL, mask_hi, j);
+                const int Lj = __shfl_sync(FULL, L, j);
+                const int hoj = __shfl_sync(FULL, it.hit_off, j);
                 const int e0j = __shfl_sync(FULL, it.e0, j);
                 const int inr = __shfl_sync(FULL, (int)in_round, j);
                 Beam bj;
@@ -320,9 +423,8 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                 bj.right = shfl_f64(bm.right, j);
                 bj.left = shfl_f64(bm.left, j);
                 bj.straddle = bj.right > bj.left;
-                const int c0 = __popc(lo);
-                if (s < total && inr && r < c0 + __popc(hi)) {      // (slot L of a beam is its hard target: filled later)
-                    const int t = r < c0 ? (int)__fns(lo, 0, r + 1) : 32 + (int)__fns(hi, 0, r + 1 - c0);
+                if (s < total && inr && r < Lj) {                   // (slot L of a beam is its hard target: filled later)
+                    const int t = a.hit_pos[hoj + r];
                     const BroadEntry en = __ldg(&a.entries[e0j + t]);
                     const ParticleRec *rp = a.rec + __float_as_int(en.w);
                     double rho;
@@ -336,27 +438,6 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             __syncwarp();
 
             if (in_round) {
-                int nh = n_masked;
-                if (L > n_masked) {                                 // long prefixes (dense tables, far targets): positions >= 64
-                    const double thd = (double)it.th32;
-                    const double thm = thd >= LSS_TWO_PI ? thd - LSS_TWO_PI : thd;
-                    const float th_rel = (float)(thm - (it.bucket + 0.5) * a.w);
-#pragma unroll 1
-                    for (int t = 64; t < plen; t++) {
-                        const BroadEntry en = __ldg(&a.entries[it.e0 + t]);
-                        if (!(fabsf(en.y - th_rel) <= en.z)) continue;
-                        const ParticleRec *rp = a.rec + __float_as_int(en.w);
-                        double rho;
-                        bool rh, lh;
-                        if (!exact_hit(rp, bm, rho, rh, lh)) continue;
-                        if (nh < L) {
-                            A0[off + nh] = rh ? bm.right : rp->t_right;
-                            A1[off + nh] = lh ? bm.left : rp->t_left;
-                            A2[off + nh] = rho;
-                        }
-                        nh++;
-                    }
-                }
                 // order by range (np.argsort, simulation.py:416); the prefix is sorted by the float32 range already, so this
                 // insertion sort almost never moves anything; equal ranges keep their prefix order
 #pragma unroll 1
