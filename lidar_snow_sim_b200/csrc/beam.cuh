@@ -64,6 +64,10 @@ struct DevArgs {
     int items_cap;
     unsigned short *hit_pos;     // prefix positions of the hits of the listed beams
     int hit_cap;
+    // optional by-product of the scan kernel for the concurrent pre-pass: the mounting-window points of calculate_plane
+    // (tools/wet_ground/planes.py:21-27) compacted per 32-row tile (prepass.cu, PrepassIO::window_staged)
+    float *win_stage;
+    int *win_tile_cnt;
 };
 
 namespace {

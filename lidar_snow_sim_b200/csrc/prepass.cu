@@ -92,69 +92,67 @@ __device__ void block_sum(double (&v)[NV], double *smem /* [NV * warps] */)
 // k_window_gather (one CTA per cloud): scans the tile counts and gathers the few thousand points contiguously.
 constexpr int WTILE = 1024;
 
-__device__ __forceinline__ bool in_window(float x, float y, float z)
-{
-    // float32 comparisons, python floats are weak scalars under NumPy 2
-    const float lim = __fsub_rn(-1.86f, __fmul_rn(0.01f, x));
-    return (z < -1.55f) && (z > lim) && (x > 10.0f) && (x < 70.0f) && (y > -3.0f) && (y < 3.0f);
-}
-
+// every warp compacts the window points of its 32 rows into the staging slot of those rows and writes their number:
+// 32-row tiles, the layout the snowfall scan kernel produces as a by-product (PrepassIO::window_staged)
 __global__ void __launch_bounds__(WTILE) k_window_tiles(PreArgs a)
 {
-    __shared__ int warp_tot[WTILE / 32];
-    const int b = blockIdx.y, tile = blockIdx.x;
+    const int b = blockIdx.y;
     const int64_t beg = a.cloud_off[b];
     const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
-    if (tile * WTILE >= n) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = tile * WTILE + tid;
+    const int w0 = blockIdx.x * WTILE + (threadIdx.x & ~31);
+    if (w0 >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int i = w0 + lane;
     float x = 0, y = 0, z = 0;
     bool in = false;
     if (i < n) {
         const float *r = a.pts + (beg + i) * 5;
         x = r[0]; y = r[1]; z = r[2];
-        in = in_window(x, y, z);
+        in = lss_in_window(x, y, z);
     }
     const unsigned m = __ballot_sync(0xffffffffu, in);
-    if (lane == 0) warp_tot[warp] = __popc(m);
-    __syncthreads();
-    int off = 0;
-    for (int wv = 0; wv < warp; wv++) off += warp_tot[wv];
     if (in) {
-        float *o = a.stage + (beg + (int64_t)tile * WTILE + off + __popc(m & ((1u << lane) - 1u))) * 3;
+        float *o = a.stage + (beg + w0 + __popc(m & ((1u << lane) - 1u))) * 3;
         o[0] = x; o[1] = y; o[2] = z;
     }
-    if (tid == WTILE - 1) a.tile_cnt[a.tile_base[b] + tile] = off + warp_tot[warp];
+    if (lane == 0) a.tile_cnt[lss_window_tile0(beg, b) + w0 / 32] = __popc(m);
 }
 
 __global__ void __launch_bounds__(1024) k_window_gather(PreArgs a)
 {
     extern __shared__ int prefix[];            // [n_tiles + 1]
+    __shared__ int wsum[32];
+    __shared__ int run_s;
     const int b = blockIdx.x;
     const int64_t beg = a.cloud_off[b];
-    const int n_tiles = a.tile_base[b + 1] - a.tile_base[b];
-    const int *cnt = a.tile_cnt + a.tile_base[b];
     const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
-    const int used_tiles = (n + WTILE - 1) / WTILE;
-    if (threadIdx.x < 32) {                    // one warp scans the tile counts
-        int run = 0;
-        for (int t0 = 0; t0 < n_tiles; t0 += 32) {
-            const int t = t0 + threadIdx.x;
-            const int v = (t < used_tiles) ? cnt[t] : 0;
-            int incl = v;
+    const int n_tiles = (n + 31) / 32;
+    const int *cnt = a.tile_cnt + lss_window_tile0(beg, b);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) run_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {          // exclusive scan of the tile counts
+        const int t = base + tid;
+        const int v = t < n_tiles ? cnt[t] : 0;
+        int incl = v;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, s); if ((int)threadIdx.x >= s) incl += o; }
-            if (t < n_tiles) prefix[t] = run + incl - v;
-            run += __shfl_sync(0xffffffffu, incl, 31);
-        }
-        if (threadIdx.x == 0) { prefix[n_tiles] = run; a.cp[b].n_window = run; }
+        for (int s = 1; s < 32; s <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= s) incl += o; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int o = run_s;
+        for (int wv = 0; wv < warp; wv++) o += wsum[wv];
+        if (t < n_tiles) prefix[t] = o + incl - v;
+        __syncthreads();
+        if (tid == 1023) run_s = o + incl;
+        __syncthreads();
     }
+    if (tid == 0) { prefix[n_tiles] = run_s; a.cp[b].n_window = run_s; }
     __syncthreads();
     const int K = prefix[n_tiles];
-    for (int o = threadIdx.x; o < K; o += blockDim.x) {
+    for (int o = tid; o < K; o += blockDim.x) {
         int lo = 0, hi = n_tiles;              // largest tile with prefix[tile] <= o
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= o) lo = mid; else hi = mid; }
-        const float *src = a.stage + (beg + (int64_t)lo * WTILE + (o - prefix[lo])) * 3;
+        const float *src = a.stage + (beg + (int64_t)lo * 32 + (o - prefix[lo])) * 3;
         float *dst = a.win + (beg + o) * 3;
         dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
     }
@@ -401,13 +399,14 @@ __device__ __forceinline__ GroundPt ground_point(const PreArgs &a, const CloudPr
 // ---- 5. ground pass 1: count, max(I/cos), first regression sums; grid (blocks, cloud) ---------------------------------------
 __global__ void __launch_bounds__(PP_TPB) k_ground_stats(PreArgs a)
 {
-    __shared__ double red[6 * (PP_TPB / 32)];
+    __shared__ double red[15 * (PP_TPB / 32)];
     __shared__ double mx[PP_TPB / 32];
     const int b = blockIdx.y;
     const CloudPre cp = a.cp[b];
     const int64_t beg = a.cloud_off[b];
     const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
-    double v[6] = {0, 0, 0, 0, 0, 0};
+    // 0 n, 1-4 first regression (shifted), 5-8 S t .. S t^4, 9-11 S cos t^k, 12-14 S d cos t^k
+    double v[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double vmax = -1e300;
     for (int i = blockIdx.x * PP_TPB + threadIdx.x; i < n; i += gridDim.x * PP_TPB) {
         const GroundPt g = ground_point(a, cp, a.pts + (beg + i) * 5);
@@ -415,16 +414,21 @@ __global__ void __launch_bounds__(PP_TPB) k_ground_stats(PreArgs a)
         const double dd = g.d - 30.0, yy = g.norm_i - 50.0;              // shifted sums (conditioning)
         v[0] += 1.0; v[1] += dd; v[2] += yy; v[3] += dd * dd; v[4] += dd * yy;
         vmax = fmax(vmax, g.norm_i);
+        const double t = (g.d - 40.0) / 30.0, t2 = t * t;
+        const double c = g.cosang, dc = g.d * g.cosang;
+        v[5] += t; v[6] += t2; v[7] += t2 * t; v[8] += t2 * t2;
+        v[9] += c; v[10] += c * t; v[11] += c * t2;
+        v[12] += dc; v[13] += dc * t; v[14] += dc * t2;
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) vmax = fmax(vmax, __shfl_down_sync(0xffffffffu, vmax, s));
     if ((threadIdx.x & 31) == 0) mx[threadIdx.x >> 5] = vmax;
-    block_sum<6>(v, red);
+    block_sum<15>(v, red);
     if (threadIdx.x == 0) {
         for (int q = 0; q < PP_TPB / 32; q++) vmax = fmax(vmax, mx[q]);
         double *p = a.partial + ((size_t)b * a.max_blocks + blockIdx.x) * 16;
-        for (int k = 0; k < 5; k++) p[k] = v[k];
-        p[5] = vmax;
+        for (int k = 0; k < 15; k++) p[k] = v[k];
+        p[15] = vmax;
     }
 }
 
@@ -454,11 +458,13 @@ __device__ __forceinline__ void warp_reduce_partials(const double *partial, int 
 __global__ void k_ground_stats_final(PreArgs a, int n_blocks)
 {
     const int b = blockIdx.x;
-    double v[5], vmax;
-    warp_reduce_partials<5>(a.partial + (size_t)b * a.max_blocks * 16, n_blocks, v, &vmax);
+    double v[15], vmax;
+    warp_reduce_partials<15>(a.partial + (size_t)b * a.max_blocks * 16, n_blocks, v, &vmax);
     if (threadIdx.x != 0) return;
     CloudPre &cp = a.cp[b];
     cp.n_ground = (int)v[0];
+    cp.mom[0] = v[0];
+    for (int k = 0; k < 10; k++) cp.mom[1 + k] = v[5 + k];
     cp.ymax = fabs(vmax);
     if (v[0] >= 3.0) {
         const double n = v[0], mx_ = v[1] / n, my_ = v[2] / n;
@@ -563,40 +569,19 @@ __global__ void __launch_bounds__(1024) k_hist_minima(PreArgs a)
 }
 
 // ---- 8. quadratic fit of noise*cos over range (simulation.py:462-467) ---------------------------------------------------------
-__global__ void __launch_bounds__(PP_TPB) k_poly_sums(PreArgs a)
-{
-    __shared__ double red[8 * (PP_TPB / 32)];
-    const int b = blockIdx.y;
-    const CloudPre cp = a.cp[b];
-    const int64_t beg = a.cloud_off[b];
-    const int n = (a.cloud_cnt ? a.cloud_cnt[b] : (int)(a.cloud_off[b + 1] - beg));
-    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (cp.n_ground >= 3) {
-        for (int i = blockIdx.x * PP_TPB + threadIdx.x; i < n; i += gridDim.x * PP_TPB) {
-            const GroundPt g = ground_point(a, cp, a.pts + (beg + i) * 5);
-            if (!g.ground) continue;
-            const double thr = a.noise_floor * (cp.pmin[0] * g.d + cp.pmin[1]) * g.cosang;   // augmentation.py:252 * cos
-            const double t = (g.d - 40.0) / 30.0;
-            const double t2 = t * t;
-            v[0] += 1.0; v[1] += t; v[2] += t2; v[3] += t2 * t; v[4] += t2 * t2;
-            v[5] += thr; v[6] += thr * t; v[7] += thr * t2;
-        }
-    }
-    block_sum<8>(v, red);
-    if (threadIdx.x == 0) {
-        double *p = a.partial + ((size_t)b * a.max_blocks + blockIdx.x) * 16;
-        for (int k = 0; k < 8; k++) p[k] = v[k];
-    }
-}
-
+// np.polyfit(d, noise * cos, 2) over the ground points with noise = noise_floor * (pmin0 * d + pmin1) (augmentation.py:252):
+// the right-hand sides S y t^k = noise_floor * (pmin0 * S d cos t^k + pmin1 * S cos t^k) come from the moment sums of the
+// first ground pass, so the fit needs no pass of its own.
 __global__ void k_poly_solve(PreArgs a, int n_blocks, double *poly_out /* [B*3] or null */, double *plane_out /* [B*4] or null */,
                              double *fit_out /* [B*8] or null */, int32_t *ymins_out /* [B*50] or null */)
 {
     const int b = blockIdx.x;
     CloudPre &cp = a.cp[b];
-    double s[8];
-    warp_reduce_partials<8>(a.partial + (size_t)b * a.max_blocks * 16, n_blocks, s, nullptr);
     if (threadIdx.x != 0) return;
+    (void)n_blocks;
+    double s[8];
+    s[0] = cp.mom[0]; s[1] = cp.mom[1]; s[2] = cp.mom[2]; s[3] = cp.mom[3]; s[4] = cp.mom[4];
+    for (int k = 0; k < 3; k++) s[5 + k] = a.noise_floor * (cp.pmin[0] * cp.mom[8 + k] + cp.pmin[1] * cp.mom[5 + k]);
     // normal equations for c0 + c1 t + c2 t^2, Gaussian elimination with partial pivoting
     double A[3][4] = {{s[0], s[1], s[2], s[5]}, {s[1], s[2], s[3], s[6]}, {s[2], s[3], s[4], s[7]}};
     bool ok = cp.n_ground >= 3;
@@ -644,7 +629,7 @@ static PrepassLayout prepass_layout(int64_t n_total, int n_clouds)
     L.cp = o;       o = align_up(o + (int64_t)sizeof(CloudPre) * n_clouds, 256);
     L.win = o;      o = align_up(o + n_total * 3 * 4, 256);
     L.stage = o;    o = align_up(o + n_total * 3 * 4, 256);
-    L.tile_cnt = o; o = align_up(o + (n_total / 1024 + n_clouds + 1) * 4, 256);
+    L.tile_cnt = o; o = align_up(o + (n_total / 32 + n_clouds + 2) * 4, 256);
     L.tile_base = o; o = align_up(o + (int64_t)(n_clouds + 1) * 4, 256);
     L.hist = o;     o = align_up(o + (int64_t)n_clouds * HIST_NX * HIST_NY * 4, 256);
     L.trial = o;    o = align_up(o + (int64_t)n_clouds * RANSAC_T * 8 * 8, 256);
@@ -657,6 +642,13 @@ static PrepassLayout prepass_layout(int64_t n_total, int n_clouds)
 }
 
 int64_t lss_prepass_ws_bytes(int64_t n_total, int n_clouds) { return prepass_layout(n_total, n_clouds).total; }
+
+void lss_prepass_window_staging(void *d_ws, int64_t n_total, int n_clouds, float **stage, int **tile_cnt)
+{
+    const PrepassLayout L = prepass_layout(n_total, n_clouds);
+    *stage = (float *)((char *)d_ws + L.stage);
+    *tile_cnt = (int *)((char *)d_ws + L.tile_cnt);
+}
 
 // Runs the whole pre-pass for a batch.  d_poly_out / d_plane_out: device [B*3] / [B*4] (either may be null).
 // h_plane_in: optional host [B*4] (w0, w1, w2, h) to use instead of the RANSAC estimate.
@@ -718,17 +710,15 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
             LSS_CUDA_CHECK(e, lss_stage_upload(e, d_plane, h_plane_in, sizeof(double) * 4 * B, stream));
             k_set_plane<<<(B + 127) / 128, 128, 0, stream>>>(a, d_plane);
         } else {
-            std::vector<int32_t> h_tb(B + 1, 0);
-            int max_tiles = 1;
-            for (int b = 0; b < B; b++) {
-                const int t = (int)((h_cloud_off[b + 1] - h_cloud_off[b] + WTILE - 1) / WTILE);
-                h_tb[b + 1] = h_tb[b] + t;
-                max_tiles = std::max(max_tiles, t);
+            const int max_tiles = (int)std::max<int64_t>(1, (max_n + WTILE - 1) / WTILE);
+            if (!io.window_staged) {
+                k_window_tiles<<<dim3(max_tiles, B), WTILE, 0, stream>>>(a);
+                e->launches++;
             }
-            LSS_CUDA_CHECK(e, lss_stage_upload(e, ws + L.tile_base, h_tb.data(), sizeof(int32_t) * (B + 1), stream));
-            k_window_tiles<<<dim3(max_tiles, B), WTILE, 0, stream>>>(a);
-            k_window_gather<<<B, 1024, sizeof(int) * (max_tiles + 1), stream>>>(a);
-            e->launches++;
+            const size_t gather_smem = sizeof(int) * ((size_t)max_tiles * (WTILE / 32) + 2);
+            if (gather_smem > 48 * 1024)
+                LSS_CUDA_CHECK(e, cudaFuncSetAttribute(k_window_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gather_smem));
+            k_window_gather<<<B, 1024, gather_smem, stream>>>(a);
             k_window_mad<<<B, 1024, 0, stream>>>(a);
             k_ransac_trials<<<dim3(RANSAC_T, B), PP_TPB, 0, stream>>>(a);
             k_ransac_refit<<<B, PP_TPB, 0, stream>>>(a);
@@ -738,9 +728,8 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
         k_ground_stats_final<<<B, 32, 0, stream>>>(a, nblk);
         k_ground_hist<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
         k_hist_minima<<<B, 1024, 0, stream>>>(a);
-        k_poly_sums<<<dim3(nblk, B), PP_TPB, 0, stream>>>(a);
         k_poly_solve<<<B, 32, 0, stream>>>(a, nblk, d_poly_out, d_plane_out, io.d_fit_out, io.d_ymins_out);
-        e->launches += 5;
+        e->launches += 4;
     }
     LSS_CUDA_CHECK(e, cudaGetLastError());
     return LSS_OK;

@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
 // (the warp runs as long as its slowest lane).  hdr: [0] entries, [LIST_CLASSES + c] class counts (from the scan kernel),
 // [2 * LIST_CLASSES + c] class cursors.  Order inside a class is arbitrary: the results do not depend on list order.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int HIT_POS_PER_BEAM = 6;                 // capacity of the hit-position array per beam of the batch
+constexpr int HIT_POS_PER_BEAM = 8;                 // capacity of the hit-position array per beam of the batch
 constexpr int SORT_PER_THREAD = 8;
 __global__ void __launch_bounds__(256) k_list_sort(const SolveItem *__restrict__ in, SolveItem *out, int *hdr, int cap)
 {
@@ -755,7 +755,7 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     //   | hit positions (u16; HIT_POS_PER_BEAM per beam of the batch on average: the surveyed densities give 1-5 occluders
     //   on a third of the beams)
     w.ovf = o;        o = align_up(o + LIST_HDR_BYTES + (int64_t)OVF_LIST_CAP * 8 + 2 * n_total * (int64_t)sizeof(SolveItem) +
-                                   (n_total * HIT_POS_PER_BEAM + 1024) * 2, 256);
+                                   (n_total * HIT_POS_PER_BEAM + 4096) * 2, 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -836,29 +836,6 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         LSS_CUDA_CHECK(e, lss_zero_async(e, z, stream));
     }
 
-    // Device pre-pass: plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given.
-    // Only k_keep needs its result, so it is forked onto one of the engine's high-priority side streams and runs next
-    // to the beam kernels (a chain of small latency-bound kernels that fits into the SMs as beam CTAs retire).
-    cudaEvent_t ev_join = nullptr;
-    if ((s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) && !s.h_thresh_poly && !s.d_thresh_poly) {
-        cudaStream_t side = nullptr;
-        cudaEvent_t ev_fork = nullptr;
-        LSS_CUDA_CHECK(e, lss_side_stream(e, &side, &ev_fork, &ev_join));
-        LSS_CUDA_CHECK(e, cudaEventRecord(ev_fork, stream));            // after the offsets upload above
-        LSS_CUDA_CHECK(e, cudaStreamWaitEvent(side, ev_fork, 0));
-        PrepassIO io;
-        io.h_plane_in = s.h_plane_in;
-        io.h_ymins_in = s.h_ymins_in;
-        io.d_poly_out = d_thresh;
-        lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
-                                        io, ws + w.prepass, w.prepass_bytes, nullptr, side);
-        const cudaError_t je = cudaEventRecord(ev_join, side);
-        if (ps != LSS_OK || je != cudaSuccess) {
-            cudaStreamWaitEvent(stream, ev_join, 0);                    // never leave the side stream dangling
-            return ps != LSS_OK ? ps : lss_fail(e, LSS_ERR_CUDA, "event record failed");
-        }
-    }
-
     DevArgs a;
     a.rec = s.ts->d_rec;
     a.entries = s.ts->d_entries;
@@ -895,7 +872,17 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     SolveItem *d_solve_list = (SolveItem *)(d_ovf_list + OVF_LIST_CAP);
     SolveItem *d_sorted_list = d_solve_list + N;
     a.hit_pos = (unsigned short *)(d_sorted_list + N);
-    a.hit_cap = (int)std::min<int64_t>(N * HIT_POS_PER_BEAM + 1024, 0x7fffffff);
+    // Device pre-pass: plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given.
+    // Only k_keep needs its result, so it runs on one of the engine's high-priority side streams next to the solve kernel (a
+    // chain of small latency-bound kernels).  Its first step, the compaction of the mounting-window points, is a by-product
+    // of the scan kernel (which reads every row anyway); the chain is forked right after the scan.
+    const bool device_prepass = (s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) &&
+                                !s.h_thresh_poly && !s.d_thresh_poly;
+    a.win_stage = nullptr;
+    a.win_tile_cnt = nullptr;
+    if (device_prepass && !s.h_plane_in) lss_prepass_window_staging(ws + w.prepass, N, B, &a.win_stage, &a.win_tile_cnt);
+    cudaEvent_t ev_join = nullptr;
+    a.hit_cap = (int)std::min<int64_t>(N * HIT_POS_PER_BEAM + 4096, 0x7fffffff);
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
         const int items_cap = (int)std::min<int64_t>(N, 0x7fffffff);
@@ -907,6 +894,25 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         {
             KernelTimer ks(e, LSS_K_SCAN, stream);
             lss_launch_scan(a, max_n, B, stream);
+        }
+        if (device_prepass) {
+            cudaStream_t side = nullptr;
+            cudaEvent_t ev_fork = nullptr;
+            LSS_CUDA_CHECK(e, lss_side_stream(e, &side, &ev_fork, &ev_join));
+            LSS_CUDA_CHECK(e, cudaEventRecord(ev_fork, stream));            // after the scan (window points staged)
+            LSS_CUDA_CHECK(e, cudaStreamWaitEvent(side, ev_fork, 0));
+            PrepassIO io;
+            io.h_plane_in = s.h_plane_in;
+            io.h_ymins_in = s.h_ymins_in;
+            io.d_poly_out = d_thresh;
+            io.window_staged = a.win_stage != nullptr;
+            lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
+                                            io, ws + w.prepass, w.prepass_bytes, nullptr, side);
+            const cudaError_t je = cudaEventRecord(ev_join, side);
+            if (ps != LSS_OK || je != cudaSuccess) {
+                cudaStreamWaitEvent(stream, ev_join, 0);                    // never leave the side stream dangling
+                return ps != LSS_OK ? ps : lss_fail(e, LSS_ERR_CUDA, "event record failed");
+            }
         }
         // 2. solve: the listed beams, sorted by work class, one warp per tile of 32 (persistent grid)
         k_list_sort<<<(unsigned)((N + 256 * SORT_PER_THREAD - 1) / (256 * SORT_PER_THREAD)), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, items_cap);

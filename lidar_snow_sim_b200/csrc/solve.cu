@@ -41,7 +41,7 @@ constexpr int SOLVE_WARPS = SOLVE_TPB / 32;
 #define LSS_SOLVE_CTAS 6
 #endif
 #ifndef LSS_SOLVE_ARENA
-#define LSS_SOLVE_ARENA 256
+#define LSS_SOLVE_ARENA 192
 #endif
 constexpr int SOLVE_CTAS_PER_SM = LSS_SOLVE_CTAS;
 constexpr int ARENA = LSS_SOLVE_ARENA;                 // slots per warp: sum over the 32 beams of (occluders + 1); more -> extra round
@@ -128,6 +128,15 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
             const float *row = &s_rows[wid][5 * lane];
             px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
         }
+    }
+    if (a.win_stage) {      // by-product for the pre-pass: this warp's mounting-window points, compacted (planes.py:21-27)
+        const bool in = active && lss_in_window(px, py, pz);
+        const unsigned m = __ballot_sync(FULL, in);
+        if (in) {
+            float *o = a.win_stage + (beg + w0 + __popc(m & ((1u << lane) - 1u))) * 3;
+            o[0] = px; o[1] = py; o[2] = pz;
+        }
+        if (lane == 0) a.win_tile_cnt[lss_window_tile0(beg, b) + w0 / 32] = __popc(m);
     }
     // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
     const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
@@ -251,14 +260,13 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
                 const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
                 const int slot = base + __popc(pm & ((1u << lane) - 1u));
                 const int hoff = hbase + lincl - L;
-                const bool fits = hoff + L <= a.hit_cap;
-                if (!fits) raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
+                const bool fits = hoff + L <= a.hit_cap;        // position array full: the beam goes to the overflow kernel
                 if (slot < a.items_cap) {
                     SolveItem it;
                     it.key = ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
                     it.e0 = e0;
                     it.hit_off = hoff;
-                    it.L = fits ? L : 0;
+                    it.L = fits ? L : 0x7fff;
                     it.th32 = th32;
                     it.pad0 = 0; it.pad1 = 0;
                     a.items_out[slot] = it;
