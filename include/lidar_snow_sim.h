@@ -245,6 +245,29 @@ LSS_API lss_status lss_fog_batch(lss_engine *e, const float *d_points, int n_fea
                                  double *d_out_info, void *d_workspace, int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_fog_workspace_bytes(int64_t n_total, int n_clouds);
 
+/* ---- LISA Monte-Carlo rain / snow augmenter ("next" row) ----------------------------------------------
+ * LISA.monte_carlo_augment (lib/LISA/python/lisa.py:293-341) with the per-return experiment monte_carlo_lisa (:34-190) on
+ * device-resident returns; caller: DenseDataset.__getitem__ (lib/OpenPCDet/pcdet/datasets/dense/dense_dataset.py:713-746).
+ *   d_points      float64[n_points * n_features] (x, y, z, intensity in [0, 1], ...), n_features >= 4 -- the reference
+ *                 feeds float64 (dense_dataset.py:732-734)
+ *   rain_rate     Rr [mm/h];  mode 0 'rain' (Marshall-Palmer), 1 'gunn' (Marshall-Gunn), 2 'sekhon' (Sekhon-Srivastava)
+ *   alpha         extinction coefficient [1/m] = LISA.alpha(LISA.Nd(D, Rr)) (:468-482), integrated by the caller from the
+ *                 Mie efficiency table (the reference's data file mie_<n>_lambda_<wl>.npz)
+ *   r_min, r_max, beam_divergence, min_diameter, range_accuracy   the LISA constructor arguments (:193-195)
+ *   signal_last   0 = 'strongest' return, 1 = 'last'
+ *   d_draw_table  float64[table_len] device or NULL.  Not NULL = the reference's fixed_seed mode (:54-55: every return
+ *                 re-seeds NumPy's MT19937 with 666): the doubles np.random.RandomState(666).random_sample(table_len)
+ *                 produces, which every return consumes from the start (one for the particle count, then ranges, then
+ *                 diameters, then pairs for the polar Gaussian).  LSS_ERR_WORKSPACE (asynchronous, lss_check_async) if a
+ *                 return needs more than table_len draws.  NULL: counter-based generator keyed by (seed, return index).
+ *   d_out         float64[n_points * (n_features + 2)]: x, y, z, intensity, label (0 lost, 1 not scattered, 2 scattered),
+ *                 intensity_diff, zeros
+ * Parity (fixed-seed): labels, particle choices and the stream position exact; values to libm rounding (pow, log, exp).  */
+LSS_API lss_status lss_lisa_batch(lss_engine *e, const double *d_points, int n_features, int64_t n_points, double rain_rate,
+                                  int mode, double alpha, double r_min, double r_max, double beam_divergence,
+                                  double min_diameter, double range_accuracy, int signal_last,
+                                  const double *d_draw_table, int table_len, uint64_t seed, double *d_out, void *stream);
+
 /* ---- point-range mask + voxelisation ("next" row) ---------------------------------------------------------
  * The detector-input stage of the reference's data path on device-resident clouds, e.g. the slot-compacted output of
  * lss_snowfall_batch / lss_wet_ground_batch, so that the augmented batch reaches the detector without a host round trip:

@@ -94,6 +94,8 @@ void lss_destroy(lss_engine *e)
     DeviceGuard g(e->device);
     for (auto &kv : e->tables) {
         cudaFree(kv.second.d_rec);
+        cudaFree(kv.second.d_tan);
+        cudaFree(kv.second.d_plane_off);
         cudaFree(kv.second.d_entries);
         cudaFree(kv.second.d_bucket_start);
     }
@@ -166,6 +168,8 @@ static lss_status upload_common(lss_engine *e, int n_planes, const double *d_xyr
     lss_status st = lss_build_tables(e, ts, d_xyr, h_off, stream);
     if (st != LSS_OK) {
         cudaFree(ts.d_rec);
+        cudaFree(ts.d_tan);
+        cudaFree(ts.d_plane_off);
         cudaFree(ts.d_entries);
         cudaFree(ts.d_bucket_start);
         return st;
@@ -214,6 +218,8 @@ lss_status lss_free_particles(lss_engine *e, int table_id)
     if (it == e->tables.end()) return lss_fail(e, LSS_ERR_NO_TABLE, "unknown table id");
     DeviceGuard g(e->device);
     cudaFree(it->second.d_rec);
+    cudaFree(it->second.d_tan);
+    cudaFree(it->second.d_plane_off);
     cudaFree(it->second.d_entries);
     cudaFree(it->second.d_bucket_start);
     e->tables.erase(it);

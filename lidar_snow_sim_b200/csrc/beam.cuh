@@ -12,13 +12,16 @@ struct __align__(16) SolveItem {
     int hit_off;                  // first of the beam's L positions in hit_pos[]
     int L;                        // occluders
     float th32;                   // beam azimuth in [0, 2 pi) as the scan used it
-    int pad0, pad1;
+    long long pbase;              // first particle of the beam's plane (entries hold plane-local indices)
 };
 
 // argument block of the per-beam kernels (global type: it crosses translation units)
 struct DevArgs {
     // tables
     const ParticleRec *rec;
+    const ParticleTan *tan;
+    const int64_t *plane_off;    // [n_planes + 1] first particle of each plane (entries hold plane-local indices)
+    float zbase;                 // decode base of the entries' half width (lss_decode)
     const BroadEntry *entries;
     const int32_t *bucket_start;
     int n_buckets;

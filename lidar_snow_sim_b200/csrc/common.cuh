@@ -15,22 +15,39 @@
 #define LSS_M_EXT 1230            // samples of the range grid R (tools/snowfall/simulation.py:111-116)
 #define LSS_ANG_MARGIN 1e-5       // rad; safety margin of the float32 broad phase (0.3 % of the 3 mrad beam)
 
-// Exact per-particle record used by the float64 narrow phase.  All angles in [0, 2 pi).
-struct __align__(16) ParticleRec {
+// Exact per-particle record used by the float64 narrow phase (24 bytes).  All angles in [0, 2 pi).
+struct ParticleRec {
     double phi;       // azimuth of the disk centre            (simulation.py:351-352)
     double rho;       // planar range sqrt(x^2 + y^2)           (simulation.py:332,413)
     double alpha;     // angular half width asin(r / rho)
-    double t_right;   // tangent angles, (right, left) ordered as geometry.py:32-80 leaves them
-    double t_left;
-    double r;         // disk radius
+};
+// ... and what only the hits need: the tangent angles, (right, left) ordered as geometry.py:32-80 leaves them (16 bytes)
+struct ParticleTan {
+    double t_right, t_left;
 };
 
-// Broad-phase entry: one per (particle, azimuth bucket it can touch).  16 B -> one LDG.128 per candidate.
-//   x = rho rounded DOWN to float32 (entries of a bucket are sorted by it)
-//   y = phi - bucket centre, wrapped to (-pi, pi]
-//   z = alpha + max_beam_divergence/2 + margin, rounded UP
-//   w = index of the ParticleRec (bit pattern of an int32)
-typedef float4 BroadEntry;
+// Broad-phase entry: one per (particle, azimuth bucket it can touch), 8 bytes:
+//   x bits  0..15  planar range in units of 2.5 mm, rounded DOWN by at least one unit (entries of a bucket are sorted by it)
+//     bits 16..31  azimuth of the centre relative to the bucket centre, in units of pi / 32767, signed
+//   y bits  0..21  index of the particle inside its plane
+//     bits 22..31  half width alpha + max_beam_divergence / 2 + margin + half an azimuth unit, as zbase * 2^(code / 32),
+//                  rounded UP (zbase = the smallest possible value, max_beam_divergence / 2 + margin)
+// Everything the float32 broad phase needs of a candidate; conservative in all three quantities.
+typedef uint2 BroadEntry;
+#define LSS_RHO_UNIT 0.0025f
+#define LSS_RHO_PER_M 400.0
+#define LSS_PHI_UNIT 9.587672516830327e-05        /* pi / 32767 */
+#define LSS_IDX_BITS 22
+struct EntryView { float x, y, z; int idx; };     // x = range bound [m], y = relative azimuth [rad], z = half width [rad]
+__device__ __forceinline__ EntryView lss_decode(const BroadEntry raw, float zbase)
+{
+    EntryView v;
+    v.x = (float)(raw.x & 0xffffu) * LSS_RHO_UNIT;
+    v.y = (float)((int)raw.x >> 16) * (float)LSS_PHI_UNIT;
+    v.z = zbase * exp2f((float)(raw.y >> LSS_IDX_BITS) * (1.0f / 32.0f));
+    v.idx = (int)(raw.y & ((1u << LSS_IDX_BITS) - 1u));
+    return v;
+}
 
 struct TableSet {
     int n_planes = 0;
@@ -38,9 +55,12 @@ struct TableSet {
     double max_div_rad = 0.0;
     int64_t n_particles = 0;
     int64_t n_entries = 0;
+    float zbase = 0.0f;                 // decode base of the entries' half width
     ParticleRec *d_rec = nullptr;       // [n_particles]
+    ParticleTan *d_tan = nullptr;       // [n_particles]
     BroadEntry *d_entries = nullptr;    // [n_entries]
     int32_t *d_bucket_start = nullptr;  // [n_planes * (n_buckets + 1)] global entry index
+    int64_t *d_plane_off = nullptr;     // [n_planes + 1] first particle of each plane
     int64_t bytes = 0;
 };
 

@@ -25,6 +25,9 @@
 // waveform window and r^2) is computed in float32 with round-to-nearest, non-fused intrinsics so it is bit-identical;
 // the geometric narrow phase, the occlusion ratios and the waveform run in float64.
 #include "beam.cuh"
+#include <cstdlib>
+
+#define LSS_CHECK_STATUS(call) do { const lss_status _st = (call); if (_st != LSS_OK) return _st; } while (0)
 
 namespace {
 
@@ -149,10 +152,11 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
             const int e0 = bs[0], e1 = bs[1];
 #pragma unroll 1
             for (int e = e0; e < e1; e++) {
-                const BroadEntry en = __ldg(&a.entries[e]);
+                const EntryView en = lss_decode(__ldg(&a.entries[e]), a.zbase);
                 if (!(en.x < d32)) break;                       // sorted by range: nothing nearer follows
                 if (!(fabsf(en.y - th_rel) <= en.z)) continue;   // float32 broad phase (conservative)
-                const ParticleRec *rp = a.rec + __float_as_int(en.w);
+                const long long pi = a.plane_off[plane] + en.idx;
+                const ParticleRec *rp = a.rec + pi;
                 const double rho = rp->rho;
                 if (!(rho < d)) continue;                        // simulation.py:345 (strict, float64)
                 const double phi = rp->phi, alpha = rp->alpha;
@@ -166,8 +170,8 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
                 if (!(inside || right_hit || left_hit)) continue;
                 if (MODE == MODE_SCAN) { L = 1; break; }           // one occluder is enough to defer the beam
                 if (L == CAP) { overflow = true; break; }
-                const double a1 = right_hit ? right : rp->t_right;   // geometry.py:26-27
-                const double a2 = left_hit ? left : rp->t_left;
+                const double a1 = right_hit ? right : a.tan[pi].t_right;   // geometry.py:26-27
+                const double a2 = left_hit ? left : a.tan[pi].t_left;
                 int j = L - 1;                                   // insertion by range (np.argsort, :416)
 #pragma unroll 1
                 while (j >= 0 && hr[j] > rho) { ha1[j + 1] = ha1[j]; ha2[j + 1] = ha2[j]; hr[j + 1] = hr[j]; j--; }
@@ -838,6 +842,9 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
 
     DevArgs a;
     a.rec = s.ts->d_rec;
+    a.tan = s.ts->d_tan;
+    a.plane_off = s.ts->d_plane_off;
+    a.zbase = s.ts->zbase;
     a.entries = s.ts->d_entries;
     a.bucket_start = s.ts->d_bucket_start;
     a.n_buckets = s.ts->n_buckets;
@@ -873,15 +880,42 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     SolveItem *d_sorted_list = d_solve_list + N;
     a.hit_pos = (unsigned short *)(d_sorted_list + N);
     // Device pre-pass: plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given.
-    // Only k_keep needs its result, so it runs on one of the engine's high-priority side streams next to the solve kernel (a
-    // chain of small latency-bound kernels).  Its first step, the compaction of the mounting-window points, is a by-product
-    // of the scan kernel (which reads every row anyway); the chain is forked right after the scan.
+    // Only k_keep needs its result, so it runs on one of the engine's high-priority side streams next to the beam kernels (a
+    // chain of small latency-bound kernels).
     const bool device_prepass = (s.flags & LSS_FLAG_THRESHOLD_FILTER) && (s.flags & LSS_FLAG_DEVICE_PREPASS) &&
                                 !s.h_thresh_poly && !s.d_thresh_poly;
+    // Where to fork it: the persistent solve kernel holds every SM's registers until its last tile, so a chain forked
+    // AFTER the scan (which would let the scan kernel compact the mounting-window points as a by-product,
+    // PrepassIO::window_staged) finds no room for its 1024-thread CTAs and becomes the critical path (measured: step
+    // 1.07 ms instead of 1.01).  Default: fork before the scan, whose CTAs retire continuously; LSS_FUSE_WINDOW=1 selects
+    // the other order for experiments.
+    static const bool fuse_window_env = getenv("LSS_FUSE_WINDOW") && getenv("LSS_FUSE_WINDOW")[0] == '1';
+    const bool fuse_window = fuse_window_env && !s.h_plane_in;
     a.win_stage = nullptr;
     a.win_tile_cnt = nullptr;
-    if (device_prepass && !s.h_plane_in) lss_prepass_window_staging(ws + w.prepass, N, B, &a.win_stage, &a.win_tile_cnt);
+    if (device_prepass && fuse_window) lss_prepass_window_staging(ws + w.prepass, N, B, &a.win_stage, &a.win_tile_cnt);
     cudaEvent_t ev_join = nullptr;
+    auto fork_prepass = [&]() -> lss_status {
+        cudaStream_t side = nullptr;
+        cudaEvent_t ev_fork = nullptr;
+        LSS_CUDA_CHECK(e, lss_side_stream(e, &side, &ev_fork, &ev_join));
+        LSS_CUDA_CHECK(e, cudaEventRecord(ev_fork, stream));        // (with fuse_window: after the scan has staged the window points)
+        LSS_CUDA_CHECK(e, cudaStreamWaitEvent(side, ev_fork, 0));
+        PrepassIO io;
+        io.h_plane_in = s.h_plane_in;
+        io.h_ymins_in = s.h_ymins_in;
+        io.d_poly_out = d_thresh;
+        io.window_staged = a.win_stage != nullptr;
+        lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
+                                io, ws + w.prepass, w.prepass_bytes, nullptr, side);
+        const cudaError_t je = cudaEventRecord(ev_join, side);
+        if (ps != LSS_OK || je != cudaSuccess) {
+            cudaStreamWaitEvent(stream, ev_join, 0);                // never leave the side stream dangling
+            return ps != LSS_OK ? ps : lss_fail(e, LSS_ERR_CUDA, "event record failed");
+        }
+        return LSS_OK;
+    };
+    if (device_prepass && !fuse_window) LSS_CHECK_STATUS(fork_prepass());
     a.hit_cap = (int)std::min<int64_t>(N * HIT_POS_PER_BEAM + 4096, 0x7fffffff);
     {
         KernelTimer kt(e, LSS_K_SNOWFALL, stream);
@@ -895,25 +929,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
             KernelTimer ks(e, LSS_K_SCAN, stream);
             lss_launch_scan(a, max_n, B, stream);
         }
-        if (device_prepass) {
-            cudaStream_t side = nullptr;
-            cudaEvent_t ev_fork = nullptr;
-            LSS_CUDA_CHECK(e, lss_side_stream(e, &side, &ev_fork, &ev_join));
-            LSS_CUDA_CHECK(e, cudaEventRecord(ev_fork, stream));            // after the scan (window points staged)
-            LSS_CUDA_CHECK(e, cudaStreamWaitEvent(side, ev_fork, 0));
-            PrepassIO io;
-            io.h_plane_in = s.h_plane_in;
-            io.h_ymins_in = s.h_ymins_in;
-            io.d_poly_out = d_thresh;
-            io.window_staged = a.win_stage != nullptr;
-            lss_status ps = lss_prepass_run(e, s.d_points, d_off, nullptr, s.h_cloud_offsets, B, 0.5, s.noise_floor, 0, 0, 1,
-                                            io, ws + w.prepass, w.prepass_bytes, nullptr, side);
-            const cudaError_t je = cudaEventRecord(ev_join, side);
-            if (ps != LSS_OK || je != cudaSuccess) {
-                cudaStreamWaitEvent(stream, ev_join, 0);                    // never leave the side stream dangling
-                return ps != LSS_OK ? ps : lss_fail(e, LSS_ERR_CUDA, "event record failed");
-            }
-        }
+        if (device_prepass && fuse_window) LSS_CHECK_STATUS(fork_prepass());
         // 2. solve: the listed beams, sorted by work class, one warp per tile of 32 (persistent grid)
         k_list_sort<<<(unsigned)((N + 256 * SORT_PER_THREAD - 1) / (256 * SORT_PER_THREAD)), 256, 0, stream>>>(d_solve_list, d_sorted_list, d_counts2, items_cap);
         a.items_in = d_sorted_list; a.items_out = nullptr;

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
     const int ch = channel_bin(pch);
     float out_l = pch;
     int e0 = 0, e1 = 0, ns = 0;
+    long long pbase = 0;                                            // first particle of the beam's plane
     bool slow = false;
     float th32 = 0.0f, th_rel = 0.0f;
     Beam bm;
@@ -162,19 +163,21 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
             const int32_t *bs = a.bucket_start + (int64_t)plane * (a.n_buckets + 1) + bk;
             e0 = bs[0];
             e1 = bs[1];
+            pbase = a.plane_off[plane];
             // ---- phase A: broad phase over the prefix of entries nearer than the target, four loads in flight --------------
             unsigned short *pos = s_pos[wid][lane];
             bool stop = false;
 #pragma unroll 1
             for (int e = e0; e < e1 && !stop; e += 4) {
-                BroadEntry en[4];
+                BroadEntry raw[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) en[q] = __ldg(&a.entries[min(e + q, e1 - 1)]);
+                for (int q = 0; q < 4; q++) raw[q] = __ldg(&a.entries[min(e + q, e1 - 1)]);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     if (stop || e + q >= e1) continue;
-                    if (!(en[q].x < d32)) { stop = true; continue; }            // sorted by range: nothing nearer follows
-                    if (!(fabsf(en[q].y - th_rel) <= en[q].z)) continue;         // float32 broad phase (conservative)
+                    const EntryView en = lss_decode(raw[q], a.zbase);
+                    if (!(en.x < d32)) { stop = true; continue; }               // sorted by range: nothing nearer follows
+                    if (!(fabsf(en.y - th_rel) <= en.z)) continue;               // float32 broad phase (conservative)
                     const int t = e + q - e0;
                     if (ns < SURV_CAP && t < 65536) pos[ns] = (unsigned short)t;
                     else slow = true;
@@ -207,16 +210,17 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
         }
         const int r = s - __shfl_sync(FULL, off, j);
         const int e0j = __shfl_sync(FULL, e0, j);
+        const long long pbj = __shfl_sync(FULL, pbase, j);
         Beam bj;
         bj.d = shfl_f64(bm.d, j);
         bj.right = shfl_f64(bm.right, j);
         bj.left = shfl_f64(bm.left, j);
         bj.straddle = bj.right > bj.left;
         if (s < total) {
-            const BroadEntry en = __ldg(&a.entries[e0j + s_pos[wid][j][r]]);
+            const BroadEntry raw = __ldg(&a.entries[e0j + s_pos[wid][j][r]]);
             double rho;
             bool rh, lh;
-            if (exact_hit(a.rec + __float_as_int(en.w), bj, rho, rh, lh)) atomicOr(&s_hit[wid][j], 1u << r);
+            if (exact_hit(a.rec + pbj + (raw.y & ((1u << LSS_IDX_BITS) - 1u)), bj, rho, rh, lh)) atomicOr(&s_hit[wid][j], 1u << r);
         }
     }
     __syncwarp();
@@ -226,12 +230,12 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
         L = 0;
 #pragma unroll 1
         for (int e = e0; e < e1; e++) {
-            const BroadEntry en = __ldg(&a.entries[e]);
+            const EntryView en = lss_decode(__ldg(&a.entries[e]), a.zbase);
             if (!(en.x < d32)) break;
             if (!(fabsf(en.y - th_rel) <= en.z)) continue;
             double rho;
             bool rh, lh;
-            if (exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) L++;
+            if (exact_hit(a.rec + pbase + en.idx, bm, rho, rh, lh)) L++;
         }
     }
     // ---- beams with occluders: warp-aggregated push to the solve list, hit positions to the position array -------------------
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
                     it.hit_off = hoff;
                     it.L = fits ? L : 0x7fff;
                     it.th32 = th32;
-                    it.pad0 = 0; it.pad1 = 0;
+                    it.pbase = pbase;
                     a.items_out[slot] = it;
                 }
                 if (fits) {
@@ -281,12 +285,12 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
                         int k = 0;
 #pragma unroll 1
                         for (int e = e0; e < e1 && k < L; e++) {
-                            const BroadEntry en = __ldg(&a.entries[e]);
+                            const EntryView en = lss_decode(__ldg(&a.entries[e]), a.zbase);
                             if (!(en.x < d32)) break;
                             if (!(fabsf(en.y - th_rel) <= en.z)) continue;
                             double rho;
                             bool rh, lh;
-                            if (exact_hit(a.rec + __float_as_int(en.w), bm, rho, rh, lh)) hp[k++] = (unsigned short)min(e - e0, 65535);
+                            if (exact_hit(a.rec + pbase + en.idx, bm, rho, rh, lh)) hp[k++] = (unsigned short)min(e - e0, 65535);
                         }
                     }
                 }
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         const int slot = tile * 32 + lane;
         const bool active = slot < cnt;
         SolveItem it;
-        it.key = 0ull; it.e0 = 0; it.hit_off = 0; it.L = 0; it.th32 = 0.0f; it.pad0 = it.pad1 = 0;
+        it.key = 0ull; it.e0 = 0; it.hit_off = 0; it.L = 0; it.th32 = 0.0f; it.pbase = 0;
         if (active) it = a.items_in[slot];
         const int b = (int)((it.key >> 32) & 0xffffu);
         const int i = (int)(it.key & 0xffffffffu);
@@ -425,6 +429,7 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                 const int Lj = __shfl_sync(FULL, L, j);
                 const int hoj = __shfl_sync(FULL, it.hit_off, j);
                 const int e0j = __shfl_sync(FULL, it.e0, j);
+                const long long pbj = __shfl_sync(FULL, it.pbase, j);
                 const int inr = __shfl_sync(FULL, (int)in_round, j);
                 Beam bj;
                 bj.d = shfl_f64(bm.d, j);
@@ -433,13 +438,19 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                 bj.straddle = bj.right > bj.left;
                 if (s < total && inr && r < Lj) {                   // (slot L of a beam is its hard target: filled later)
                     const int t = a.hit_pos[hoj + r];
-                    const BroadEntry en = __ldg(&a.entries[e0j + t]);
-                    const ParticleRec *rp = a.rec + __float_as_int(en.w);
+                    const BroadEntry raw = __ldg(&a.entries[e0j + t]);
+                    const long long pi = pbj + (raw.y & ((1u << LSS_IDX_BITS) - 1u));
                     double rho;
                     bool rh, lh;
-                    exact_hit(rp, bj, rho, rh, lh);
-                    A0[s] = rh ? bj.right : rp->t_right;            // geometry.py:26-27
-                    A1[s] = lh ? bj.left : rp->t_left;
+                    exact_hit(a.rec + pi, bj, rho, rh, lh);
+                    double a1 = bj.right, a2 = bj.left;             // geometry.py:26-27: a limit ray the disk crosses clips
+                    if (!rh || !lh) {
+                        const ParticleTan tn = a.tan[pi];
+                        if (!rh) a1 = tn.t_right;
+                        if (!lh) a2 = tn.t_left;
+                    }
+                    A0[s] = a1;
+                    A1[s] = a2;
                     A2[s] = rho;
                 }
             }

@@ -8,6 +8,10 @@
 // every bucket whose angular extent, grown by (alpha + max_beam_divergence/2 + margin) on both sides, contains its
 // centre azimuth -- so a beam only ever has to look at the ONE bucket its own azimuth falls into.  Inside a bucket
 // entries are sorted by planar range, so the strict "particle nearer than the target" test (:345) becomes a prefix.
+//
+// Size (round 2): 8-byte quantised broad-phase entries (common.cuh: BroadEntry) + 24-byte exact records + 16-byte
+// tangent angles that only hits touch = 8 * 2.2 + 40 = 58 bytes per particle, of which 42 are on the scan kernel's path
+// (round 1: 80): at 18 k disks per plane the scan's working set is 48 MB of the 126 MB L2, next to the streamed rows.
 #include "common.cuh"
 
 namespace {
@@ -65,6 +69,8 @@ struct BuildParams {
     int n_buckets;
     double half_div_margin;     // max_div/2 + margin
     ParticleRec *rec;
+    ParticleTan *tan;
+    float zbase;
     int32_t *span_lo;           // [n_particles] first bucket
     int32_t *span_n;            // [n_particles] number of buckets (0 = particle ignored)
     int32_t *counts;            // [n_planes*n_buckets]
@@ -94,14 +100,15 @@ __global__ void k_particle_records(BuildParams bp)
     double phi = atan2(y, x);
     if (phi < 0) phi += LSS_TWO_PI;
     rec.phi = phi;
-    rec.r = r;
     bool ok = isfinite(x) && isfinite(y) && isfinite(r) && (r > 0.0) && (rec.rho > r);
     double tr = 0, tl = 0;
     if (ok) ok = tangent_angles(x, y, r, phi, tr, tl);
     rec.alpha = ok ? asin(r / rec.rho) : 0.0;
-    rec.t_right = tr;
-    rec.t_left = tl;
     bp.rec[p] = rec;
+    ParticleTan tn;
+    tn.t_right = tr;
+    tn.t_left = tl;
+    bp.tan[p] = tn;
     int lo = 0, n = 0;
     if (ok) {
         double w = LSS_TWO_PI / bp.n_buckets;
@@ -137,8 +144,16 @@ __global__ void k_fill_entries(BuildParams bp)
     int plane = plane_of(bp.plane_off, bp.n_planes, p);
     ParticleRec rec = bp.rec[p];
     double w = LSS_TWO_PI / bp.n_buckets;
-    float rho_lo = __double2float_rd(rec.rho);
-    float aexp = __double2float_ru(rec.alpha + bp.half_div_margin);
+    // range: units of 2.5 mm, one unit below the floor (so that the float32 product unit * code stays below rho)
+    long long rq = (long long)floor(rec.rho * LSS_RHO_PER_M) - 1;
+    rq = rq < 0 ? 0 : (rq > 65535 ? 65535 : rq);
+    // half width: what the registration span used + half an azimuth unit for the rounding of the relative azimuth, as
+    // the smallest code c with zbase * 2^(c / 32) >= it (float32 decode, checked below)
+    const float want = __double2float_ru(rec.alpha + bp.half_div_margin + 0.5 * LSS_PHI_UNIT);
+    int zc = (int)ceil(32.0 * log2((double)want / (double)bp.zbase));
+    zc = zc < 0 ? 0 : zc;
+    while (zc < 1023 && bp.zbase * exp2f((float)zc * (1.0f / 32.0f)) < want) zc++;
+    const long long local = p - bp.plane_off[plane];
     for (int k = 0; k < n; k++) {
         int b = lo + k;
         if (b >= bp.n_buckets) b -= bp.n_buckets;
@@ -147,11 +162,10 @@ __global__ void k_fill_entries(BuildParams bp)
         if (rel > LSS_PI) rel -= LSS_TWO_PI;
         if (rel <= -LSS_PI) rel += LSS_TWO_PI;
         int pos = atomicAdd(&bp.cursor[plane * bp.n_buckets + b], 1);
+        const int pq = (int)rint(rel / LSS_PHI_UNIT);                       // |pq| <= 32767
         BroadEntry en;
-        en.x = rho_lo;
-        en.y = (float)rel;
-        en.z = aexp;
-        en.w = __int_as_float((int)p);
+        en.x = (unsigned)rq | ((unsigned)(pq & 0xffff) << 16);
+        en.y = (unsigned)local | ((unsigned)zc << LSS_IDX_BITS);
         bp.entries[(int64_t)bp.bucket_start[plane * (bp.n_buckets + 1) + b] + pos] = en;
     }
 }
@@ -166,13 +180,15 @@ __global__ void k_sort_buckets(BuildParams bp)
     int e = bp.bucket_start[plane * (bp.n_buckets + 1) + b + 1];
     BroadEntry *a = bp.entries + s;
     int n = e - s;
+    const unsigned idx_mask = (1u << LSS_IDX_BITS) - 1u;
     for (int i = 1; i < n; i++) {
         BroadEntry key = a[i];
-        int ki = __float_as_int(key.w);
+        const unsigned kr = key.x & 0xffffu, ki = key.y & idx_mask;
         int j = i - 1;
         while (j >= 0) {
             BroadEntry c = a[j];
-            bool greater = (c.x > key.x) || (c.x == key.x && __float_as_int(c.w) > ki);
+            const unsigned cr = c.x & 0xffffu;
+            bool greater = (cr > kr) || (cr == kr && (c.y & idx_mask) > ki);
             if (!greater) break;
             a[j + 1] = c;
             j--;
@@ -191,8 +207,11 @@ lss_status lss_build_tables(lss_engine *e, TableSet &ts, const double *d_xyr, co
     ts.n_particles = np;
     if (np <= 0) return lss_fail(e, LSS_ERR_INVALID_ARG, "empty particle table set");
     if (np >= (1LL << 31)) return lss_fail(e, LSS_ERR_INVALID_ARG, "too many particles");
+    for (int k = 0; k < n_planes; k++)
+        if (h_plane_offsets[k + 1] - h_plane_offsets[k] >= (1LL << LSS_IDX_BITS))
+            return lss_fail(e, LSS_ERR_INVALID_ARG, "more than 4 194 303 particles in one plane");
 
-    int64_t *d_off = nullptr;
+    int64_t *d_off = nullptr;                     // kept: ts.d_plane_off
     int32_t *d_span_lo = nullptr, *d_span_n = nullptr, *d_counts = nullptr, *d_cursor = nullptr;
     LSS_CUDA_CHECK(e, cudaMalloc(&d_off, sizeof(int64_t) * (n_planes + 1)));
     LSS_CUDA_CHECK(e, cudaMalloc(&d_span_lo, sizeof(int32_t) * np));
@@ -200,6 +219,7 @@ lss_status lss_build_tables(lss_engine *e, TableSet &ts, const double *d_xyr, co
     LSS_CUDA_CHECK(e, cudaMalloc(&d_counts, sizeof(int32_t) * n_planes * nb));
     LSS_CUDA_CHECK(e, cudaMalloc(&d_cursor, sizeof(int32_t) * n_planes * nb));
     LSS_CUDA_CHECK(e, cudaMalloc(&ts.d_rec, sizeof(ParticleRec) * np));
+    LSS_CUDA_CHECK(e, cudaMalloc(&ts.d_tan, sizeof(ParticleTan) * np));
     LSS_CUDA_CHECK(e, cudaMalloc(&ts.d_bucket_start, sizeof(int32_t) * n_planes * (nb + 1)));
     LSS_CUDA_CHECK(e, cudaMemcpyAsync(d_off, h_plane_offsets, sizeof(int64_t) * (n_planes + 1),
                                       cudaMemcpyHostToDevice, stream));
@@ -213,6 +233,9 @@ lss_status lss_build_tables(lss_engine *e, TableSet &ts, const double *d_xyr, co
     bp.n_buckets = nb;
     bp.half_div_margin = ts.max_div_rad / 2 + LSS_ANG_MARGIN;
     bp.rec = ts.d_rec;
+    bp.tan = ts.d_tan;
+    ts.zbase = (float)(ts.max_div_rad / 2 + LSS_ANG_MARGIN);
+    bp.zbase = ts.zbase;
     bp.span_lo = d_span_lo;
     bp.span_n = d_span_n;
     bp.counts = d_counts;
@@ -249,12 +272,12 @@ lss_status lss_build_tables(lss_engine *e, TableSet &ts, const double *d_xyr, co
     e->launches += 2;
     LSS_CUDA_CHECK(e, cudaGetLastError());
     LSS_CUDA_CHECK(e, cudaStreamSynchronize(stream));
-    cudaFree(d_off);
+    ts.d_plane_off = d_off;
     cudaFree(d_span_lo);
     cudaFree(d_span_n);
     cudaFree(d_counts);
     cudaFree(d_cursor);
-    ts.bytes = (int64_t)sizeof(ParticleRec) * np + (int64_t)sizeof(BroadEntry) * total +
-               (int64_t)sizeof(int32_t) * n_planes * (nb + 1);
+    ts.bytes = (int64_t)(sizeof(ParticleRec) + sizeof(ParticleTan)) * np + (int64_t)sizeof(BroadEntry) * total +
+               (int64_t)sizeof(int32_t) * n_planes * (nb + 1) + (int64_t)sizeof(int64_t) * (n_planes + 1);
     return LSS_OK;
 }
