@@ -58,6 +58,7 @@ FIXED_POLY = (2e-3, -0.3, 12.0)     # only used with --host-threshold
 CPU_CLOUDS_PER_STEP = 32
 CPU_THREADS_PER_CLOUD = 4
 MIN_TIMED_MS = 1000.0
+STEPS_IN_FLIGHT = 1                 # device-resident leg: consecutive steps on alternating streams (1 = strictly serial)
 
 
 def load_peaks():
@@ -298,6 +299,8 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-gather', action='store_true', help='N > 1: replicas only, skip the all-gather (debug)')
     ap.add_argument('--min-timed-ms', type=float, default=MIN_TIMED_MS)
+    ap.add_argument('--streams', type=int, default=STEPS_IN_FLIGHT, choices=[1, 2],
+                    help='steps in flight in the device-resident leg: consecutive steps alternate between this many streams')
     ap.add_argument('--e2e-inflight', type=int, default=3, help='batches in flight in the e2e leg (1..3)')
     ap.add_argument('--e2e-chunks', type=int, default=2, help='chunks of the host-to-host pipeline (e2e leg)')
     args = ap.parse_args()
@@ -358,24 +361,64 @@ def main():
         from lidar_snow_sim_b200.distributed import BatchGather
         gather = BatchGather(N, B, dev, depth=2)
 
+    # config 2: the wet stage of step k runs on its own stream next to the snow stage of step k + 1 (both are chains of
+    # latency-bound kernels; the wet pre-pass can only start when the snow output exists).  Double-buffered, stream-ordered.
+    n_streams = max(1, min(2, args.streams))
+    step_streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else None
+    step_ws = None
+    if step_streams is not None:       # one engine workspace per stream: the steps in flight must not share scratch
+        need = eng.lib.lss_snowfall_workspace_bytes(N, B)
+        step_ws = [torch.empty(int(need) + 256, dtype=torch.uint8, device=dev) for _ in range(n_streams)]
+    step_done = [None, None]
+    wet_stream = torch.cuda.Stream(device=dev) if fused_wet else None
+    wet_outs = [{}, {}]
+    ev_snow = [torch.cuda.Event() for _ in range(2)]
+    ev_wet = [None, None]
+
     def step(k):
         """One pass of the augment() pipeline over this rank's batch (config 2: + wet ground on the snow output); with
         N > 1 followed by the all-gather of the augmented batch, overlapping the next step's kernels
         (double-buffered)."""
         j = k & 1
+        if step_streams is not None:                       # consecutive steps alternate between the streams
+            with torch.cuda.stream(step_streams[j % n_streams]):
+                return _step_on_current_stream(j)
+        return _step_on_current_stream(j)
+
+    def _step_on_current_stream(j):
         if gather is not None:
             gather.wait(j)
+        cur = torch.cuda.current_stream(dev)
+        if fused_wet and ev_wet[j] is not None:
+            cur.wait_event(ev_wet[j])                      # the wet stage two steps ago still reads outs[j]
         r = eng.snowfall_batch(tid, d_pts[j], off, d_orders[j], DIV_DEG, thresh_poly=poly, device_prepass=device_prepass,
-                               out=outs[j])
+                               out=outs[j], workspace=None if step_ws is None else step_ws[j % n_streams])
+        if step_streams is not None:
+            step_done[j] = torch.cuda.Event()
+            step_done[j].record(cur)
         if fused_wet:
-            r = eng.wet_ground_batch(r['points'], off, counts=r['counts'], water_height=WATER_HEIGHT, replace=False)
+            ev_snow[j].record(cur)
+            with torch.cuda.stream(wet_stream):
+                wet_stream.wait_event(ev_snow[j])
+                r = eng.wet_ground_batch(r['points'], off, counts=r['counts'], water_height=WATER_HEIGHT, replace=False,
+                                         out=wet_outs[j])
+                ev_wet[j] = torch.cuda.Event()
+                ev_wet[j].record(wet_stream)
         if gather is not None:
             gather.start(j, r['points'], r['counts'])
         return r
 
     def drain():
+        if step_streams is not None:
+            for ev in step_done:
+                if ev is not None:
+                    torch.cuda.current_stream(dev).wait_event(ev)
         if gather is not None:
             gather.wait_all()
+        if fused_wet:
+            for ev in ev_wet:
+                if ev is not None:
+                    torch.cuda.current_stream(dev).wait_event(ev)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -389,6 +432,9 @@ def main():
         e1 = torch.cuda.Event(enable_timing=True)
         sync_all()
         e0.record()
+        if step_streams is not None:
+            for st in step_streams:
+                st.wait_event(e0)
         for k in range(n_steps):
             step(k0 + k)
         drain()
@@ -577,7 +623,7 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu,
             'repeats': repeats, 'timed_region_ms': float(np.sum(times)),
             'ms_per_step_min': float(np.min(times)) / args.steps, 'ms_per_step_max': float(np.max(times)) / args.steps,
-            'theta_label_mismatch': theta_info,
+            'theta_label_mismatch': theta_info, 'steps_in_flight': n_streams,
             'engine': {'prepass': 'device' if device_prepass else 'DEBUG: fixed host-supplied threshold polynomial',
                        'table_particles': tinfo['n_particles'], 'table_index_bytes': tinfo['bytes'],
                        'gather': None if gather is None else gather.kind}}

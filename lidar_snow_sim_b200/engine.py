@@ -306,7 +306,7 @@ class SnowfallEngine:
 
     def wet_ground_batch(self, points, cloud_offsets, counts=None, water_height=0.001, pavement_depth=0.0012,
                          noise_floor=0.7, power_factor=15, flat_earth=False, delta=0.5, replace=True, plane=None,
-                         want_intensity64=False, ymins=None):
+                         want_intensity64=False, ymins=None, out=None):
         """
         Batched ground_water_augmentation() on device-resident clouds (current stream, no synchronisation).
         counts: optional CUDA int32 (B,) valid rows per cloud slot (fused snow -> wet path).
@@ -319,11 +319,14 @@ class SnowfallEngine:
         pl = None if plane is None else np.ascontiguousarray(plane, dtype=np.float64).reshape(B, 4)
         ym = None if ymins is None else np.ascontiguousarray(ymins, dtype=np.int32).reshape(B, 50)
         with torch.cuda.device(self.device):
-            out = dict(points=torch.empty((N, 5), dtype=torch.float32, device=self.device),
-                       counts=torch.empty((B,), dtype=torch.int32, device=self.device),
-                       passthrough=torch.empty((B,), dtype=torch.int32, device=self.device),
-                       plane=torch.empty((B, 4), dtype=torch.float64, device=self.device))
-            if want_intensity64:
+            if out is None:
+                out = {}
+            if 'points' not in out:                            # (pass the returned dict back in as `out` to reuse the buffers)
+                out.update(points=torch.empty((N, 5), dtype=torch.float32, device=self.device),
+                           counts=torch.empty((B,), dtype=torch.int32, device=self.device),
+                           passthrough=torch.empty((B,), dtype=torch.int32, device=self.device),
+                           plane=torch.empty((B, 4), dtype=torch.float64, device=self.device))
+            if want_intensity64 and 'intensity64' not in out:
                 out['intensity64'] = torch.empty((N,), dtype=torch.float64, device=self.device)
             need = self.lib.lss_wet_ground_workspace_bytes(N, B)
             if getattr(self, '_ws_wet', None) is None or self._ws_wet.numel() < need:
@@ -331,7 +334,8 @@ class SnowfallEngine:
             st = self.lib.lss_wet_ground_batch(
                 self.h, _ptr(points), _ptr(off), _ptr(counts), B, float(water_height), float(pavement_depth),
                 float(noise_floor), float(power_factor), 1 if flat_earth else 0, float(delta), 1 if replace else 0,
-                _ptr(pl), _ptr(ym), _ptr(out['points']), _ptr(out.get('intensity64')), _ptr(out['counts']),
+                _ptr(pl), _ptr(ym), _ptr(out['points']), _ptr(out.get('intensity64')) if want_intensity64 else None,
+                _ptr(out['counts']),
                 _ptr(out['passthrough']), _ptr(out['plane']), _ptr(self._ws_wet), int(self._ws_wet.numel()),
                 self._stream())
         _lib.check(st, self.h)
