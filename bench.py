@@ -626,7 +626,8 @@ def main():
             'theta_label_mismatch': theta_info, 'steps_in_flight': n_streams,
             'engine': {'prepass': 'device' if device_prepass else 'DEBUG: fixed host-supplied threshold polynomial',
                        'table_particles': tinfo['n_particles'], 'table_index_bytes': tinfo['bytes'],
-                       'gather': None if gather is None else gather.kind}}
+                       'gather': None if gather is None else gather.kind,
+                       'gather_fallback': None if gather is None else getattr(gather, 'fallback_reason', None)}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
