@@ -329,7 +329,7 @@ def main():
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
 
     numa_cpus = None
-    if world > 1 and os.environ.get('LSS_NUMA_BIND', '1') != '0':
+    if world > 1 and os.environ.get('LSS_NUMA_BIND', '0') == '1':
         try:
             from lidar_snow_sim_b200.distributed import bind_host_to_gpu
             numa_cpus = bind_host_to_gpu(local_rank)      # pinned host buffers land on the GPU's own NUMA node

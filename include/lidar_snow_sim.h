@@ -334,6 +334,9 @@ LSS_API int64_t lss_sample_particles_workspace_bytes(int n_planes, int64_t n_can
 LSS_API lss_status lss_set_profiling(lss_engine *e, int enable);
 LSS_API lss_status lss_kernel_times(lss_engine *e, int reset, double *h_ms, int64_t *h_calls, int n);
 LSS_API const char *lss_kernel_name(int kernel);
+/* test hook: the beam azimuth the kernels compute when no d_theta is supplied, (float)atan2((double)y, (double)x)
+ * (simulation.py:91), element-wise on device arrays of n float32 values                                              */
+LSS_API lss_status lss_debug_azimuth(lss_engine *e, const float *d_y, const float *d_x, int64_t n, float *d_out, void *stream);
 /* test hook: the engine's range grid R = np.round(np.linspace(0, 120 + c*tau_h, 1230), 2) (simulation.py:111-116),
  * 1230 doubles written to h_out.  Host only, needs no GPU.                                                          */
 LSS_API lss_status lss_debug_range_grid(double *h_out);

@@ -715,6 +715,25 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
 
 }  // namespace
 
+namespace {
+__global__ void k_debug_azimuth(const float *y, const float *x, float *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = azimuth32(y[i], x[i]);
+}
+}  // namespace
+
+extern "C" lss_status lss_debug_azimuth(lss_engine *e, const float *d_y, const float *d_x, int64_t n, float *d_out, void *stream)
+{
+    if (!e || !d_y || !d_x || !d_out || n < 0) return LSS_ERR_INVALID_ARG;
+    if (n == 0) return LSS_OK;
+    DeviceGuard g(e->device);
+    k_debug_azimuth<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_y, d_x, d_out, n);
+    e->launches++;
+    LSS_CUDA_CHECK(e, cudaGetLastError());
+    return LSS_OK;
+}
+
 void lss_launch_scan(const DevArgs &a, int64_t max_rows, int n_clouds, cudaStream_t stream)
 {
     const dim3 grid((unsigned)((max_rows + SNOW_TPB - 1) / SNOW_TPB), (unsigned)n_clouds);

@@ -482,3 +482,28 @@ def test_augment_snowfall_rate_signature(engine, tmp_path, monkeypatch):
     assert s1 == s2 == s3 and np.array_equal(a1, a2) and np.array_equal(a1, a3) and a1.shape[0] > 0
     with pytest.raises(FileNotFoundError):
         sim.augment(pc, 'gunn_1.0_2.0', DIV, engine=engine)
+
+
+def test_device_azimuth_is_the_rounded_float64_atan2(engine):
+    """The kernels' beam azimuth (fast table + series path with a library fall-back near float32 rounding boundaries) equals
+    float32(atan2(float64 y, float64 x)) bit for bit -- on the bench cloud, on random arguments and on special values."""
+    import ctypes
+    from lidar_snow_sim_b200.engine import _ptr
+    rng = np.random.default_rng(3)
+    pc = synthetic_cloud(seed=8, n_azimuth=2048)
+    xs = [pc[:, 0], rng.uniform(-120, 120, 2_000_000).astype(np.float32), (10.0 ** rng.uniform(-20, 20, 200_000)).astype(np.float32),
+          np.array([0, 0, 1, -1, 0.0, -0.0, 1e-30, 3e38, np.inf, -np.inf, np.nan, 1, 1, -1, 5, -5], dtype=np.float32)]
+    ys = [pc[:, 1], rng.uniform(-120, 120, 2_000_000).astype(np.float32), (-(10.0 ** rng.uniform(-20, 20, 200_000))).astype(np.float32),
+          np.array([0, 1, 0, 0, -0.0, -0.0, 1e-30, 3e38, np.inf, 1, 1, np.nan, 1, -1, 5e-8, -5e-8], dtype=np.float32)]
+    x = np.concatenate(xs)
+    y = np.concatenate(ys)
+    d_x, d_y = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out = torch.empty_like(d_x)
+    st = engine.lib.lss_debug_azimuth(engine.h, _ptr(d_y), _ptr(d_x), x.shape[0], _ptr(out), engine._stream())
+    assert st == 0
+    engine.check()
+    got = out.cpu().numpy()
+    with np.errstate(invalid='ignore'):
+        want = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32)
+    same = (got.view(np.int32) == want.view(np.int32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (int((~same).sum()), x[~same][:5], y[~same][:5], got[~same][:5], want[~same][:5])
