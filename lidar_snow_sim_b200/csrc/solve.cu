@@ -24,10 +24,10 @@
 //   * waveform: sin(pi (R_k - r) / (c tau)) = sin(pi a_k) cos(pi b) - cos(pi a_k) sin(pi b) with a_k = R_k / (c tau) from a
 //     1230-entry table (host, extended precision) and b = r / (c tau) evaluated once per pulse (one sincospi), so a
 //     sample costs a 16-byte load and six float64 operations instead of a sinpi;
-//   * an isolated pulse is unimodal: its owner evaluates the three samples around the peak itself; groups of
-//     overlapping pulses are summed over their whole union window (in dict order, like the reference's i[k] +=) by ALL 32
-//     lanes of the warp, one group at a time, 128 samples per pass in four register accumulators per lane, and reduced
-//     with three integer warp reductions (first maximum wins, np.argmax).
+//   * the sample axis is cut into pieces with a fixed set of active pulses; on a piece the summed waveform is a single
+//     sinusoid, so only the samples around its analytic peak and the piece's ends are evaluated (exactly, in dict order
+//     like the reference's i[k] +=; first maximum wins, np.argmax) -- a handful of samples per piece instead of whole
+//     windows, lane-local, 32 beams in parallel.
 //
 // Beams the arena cannot take (more than SOLVE_LCAP occluders) go to the overflow list and are redone by the
 // round-1 list kernel (snowfall.cu, k_snowfall<SLOW_CAP, MODE_LIST>), which has no such limit below 128.
@@ -558,113 +558,78 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             }
 
             // ---- argmax of the summed waveform (simulation.py:148-153) -----------------------------------------------------
-            // Only samples inside some pulse window are non-zero.  Pulses whose windows overlap form a group whose samples
-            // are summed in full; an isolated pulse A sin^2(pi (R - r)/(c tau)) is unimodal and symmetric about
-            // r + c tau / 2, so its maximum over the grid is at one of the three samples around the sample nearest to the peak.
-            auto update = [&](double v, int k) {
-                if (v > best || (v == best && v > 0.0 && k < kbest)) { best = v; kbest = k; }
-            };
-            int j = 0;
-            bool have = false;
-            int g_klo = 0, g_khi = 0, g_q0 = 0, g_q1 = 0;
-            auto advance = [&]() {        // isolated pulses are solved on the way; stops at the next group
-                have = false;
+            // Only samples inside some pulse window are non-zero.  Pulse ranges ascend, so first and end samples of the
+            // windows ascend too and a sweep over them cuts the sample axis into PIECES on which the set of active pulses is
+            // a fixed index range [qa, qb].  On a piece the waveform is ONE sinusoid of period c tau (29.96 samples; a piece
+            // is shorter than a window, 31 samples):
+            //     sum_q A_q sin^2(pi (R - r_q) / (c tau)) = C - |Z| / 2 * cos(2 pi R / (c tau) - arg Z),   Z = sum_q A_q e^(2 pi i r_q / (c tau))
+            // so its maximum over the piece's samples is at one of the samples around the analytic peak R* (if inside) or at an
+            // end of the piece.  Those few candidates -- not the whole window -- are evaluated exactly, float64, pulses summed in
+            // dict order like the reference's i[k] +=, and the first maximum wins (np.argmax).  R* only SELECTS candidates
+            // (float32 is ample: the grid is 0.1 m); two samples either side absorb the grid's rounding to 0.01 m.  If the
+            // pulses cancel (|Z| tiny: every sample of the piece has the same value up to rounding) the whole piece is evaluated.
+            // A single pulse peaks at its stored sample k0.  Everything is lane-local: 32 beams advance in parallel, where the
+            // round-2a kernel summed whole group windows with all lanes, one group at a time (47 % of its instructions).
+            if (n_pulses > 0) {
+                const float step = (float)((120 + ctau) / (double)(LSS_M_EXT - 1));
+                const float ctau_f = (float)ctau;
+                int qa = 0, qb = -1, nxt = 0;
+                int k = (int)(W[off] & 2047u);
 #pragma unroll 1
-                while (j < n_pulses) {
-                    const unsigned long long w0 = W[off + j];
-                    const int ks = (int)(w0 & 2047u), ke = (int)((w0 >> 11) & 2047u), k0 = (int)((w0 >> 22) & 2047u);
-                    int g1 = j, k_lo = ks, k_hi = ke;
+                for (;;) {
 #pragma unroll 1
-                    while (g1 + 1 < n_pulses) {
-                        const unsigned long long w1 = W[off + g1 + 1];
-                        const int ks1 = (int)(w1 & 2047u);
-                        if (!(ks1 < k_hi)) break;
-                        g1++;
-                        k_lo = min(k_lo, ks1);
-                        k_hi = max(k_hi, (int)((w1 >> 11) & 2047u));
+                    while (nxt < n_pulses && (int)(W[off + nxt] & 2047u) <= k) { qb = nxt; nxt++; }
+#pragma unroll 1
+                    while (qa <= qb && (int)((W[off + qa] >> 11) & 2047u) <= k) qa++;
+                    if (qa > qb) {
+                        if (nxt >= n_pulses) break;
+                        k = (int)(W[off + nxt] & 2047u);
+                        continue;
                     }
-                    if (g1 > j) {
-                        g_klo = k_lo; g_khi = k_hi; g_q0 = off + j; g_q1 = off + g1;
-                        j = g1 + 1;
-                        have = true;
-                        return;
-                    }
-                    const double amp = A0[off + j], sb = A1[off + j], cb = A3[off + j];
-                    const int lo = max(ks, k0 - 1), hi = min(ke, k0 + 2);
+                    int pend = (int)((W[off + qa] >> 11) & 2047u);                 // the oldest active pulse ends first
+                    if (nxt < n_pulses) pend = min(pend, (int)(W[off + nxt] & 2047u));
+                    const int lo = k, hi = pend;                                    // piece [lo, hi), active pulses qa .. qb
+                    auto eval = [&](int c) {
+                        const double2 t = __ldg(&a.wtab[c]);
+                        double v = 0.0;
 #pragma unroll 1
-                    for (int k = lo; k < hi; k++) {
-                        const double2 t = __ldg(&a.wtab[k]);
-                        const double sn = t.x * cb - t.y * sb;
-                        update(amp * (sn * sn), k);
-                    }
-                    j++;
-                }
-            };
-            if (n_pulses > 0) advance();
-            __syncwarp();
-            unsigned gm;
-            while ((gm = __ballot_sync(FULL, have)) != 0u) {
-#pragma unroll 1
-                for (unsigned mm = gm; mm; mm &= mm - 1) {
-                    const int src = __ffs(mm) - 1;
-                    const int klo = __shfl_sync(FULL, g_klo, src), khi = __shfl_sync(FULL, g_khi, src);
-                    const int q0 = __shfl_sync(FULL, g_q0, src), q1 = __shfl_sync(FULL, g_q1, src);
-                    double gb = 0.0;
-                    unsigned gk = 0u;
-#pragma unroll 1
-                    for (int base = klo; base < khi; base += 128) {
-                        // four samples per lane: k = base + lane + 32 m, accumulators in registers
-                        const int kk = base + lane;
-                        const double2 z = make_double2(0.0, 0.0);
-                        const double2 t0 = kk < khi ? __ldg(&a.wtab[kk]) : z;
-                        const double2 t1 = kk + 32 < khi ? __ldg(&a.wtab[kk + 32]) : z;
-                        const double2 t2 = kk + 64 < khi ? __ldg(&a.wtab[kk + 64]) : z;
-                        const double2 t3 = kk + 96 < khi ? __ldg(&a.wtab[kk + 96]) : z;
-                        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-#pragma unroll 1
-                        for (int q = q0; q <= q1; q++) {                // pulses in dict order, like the reference's i[k] +=
-                            const unsigned long long wq = W[q];
-                            const int ks = (int)(wq & 2047u), ke = (int)((wq >> 11) & 2047u);
-                            if (ke <= base || ks >= base + 128) continue;   // (uniform over the warp)
-                            const double amp = A0[q], sb = A1[q], cb = A3[q];
-                            if (ks < base + 32 && ke > base && kk >= ks && kk < ke) {
-                                const double sn = t0.x * cb - t0.y * sb;
-                                v0 += amp * (sn * sn);
-                            }
-                            if (ks < base + 64 && ke > base + 32 && kk + 32 >= ks && kk + 32 < ke) {
-                                const double sn = t1.x * cb - t1.y * sb;
-                                v1 += amp * (sn * sn);
-                            }
-                            if (ks < base + 96 && ke > base + 64 && kk + 64 >= ks && kk + 64 < ke) {
-                                const double sn = t2.x * cb - t2.y * sb;
-                                v2 += amp * (sn * sn);
-                            }
-                            if (ke > base + 96 && kk + 96 >= ks && kk + 96 < ke) {
-                                const double sn = t3.x * cb - t3.y * sb;
-                                v3 += amp * (sn * sn);
-                            }
+                        for (int q = off + qa; q <= off + qb; q++) {
+                            const double sn = t.x * A3[q] - t.y * A1[q];
+                            v += A0[q] * (sn * sn);
                         }
-                        // this lane's first maximum (ascending sample index), then the warp's: non-negative doubles order
-                        // like their bit patterns -> max high word, max low word among those, min sample index among the
-                        // exact ties = the first maximum, like np.argmax
-                        double v = v0;
-                        int k = kk;
-                        if (v1 > v) { v = v1; k = kk + 32; }
-                        if (v2 > v) { v = v2; k = kk + 64; }
-                        if (v3 > v) { v = v3; k = kk + 96; }
-                        const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
-                        const unsigned vhi = (unsigned)(vb >> 32), vlo = (unsigned)vb;
-                        const unsigned mhi = __reduce_max_sync(FULL, vhi);
-                        const unsigned mlo = __reduce_max_sync(FULL, vhi == mhi ? vlo : 0u);
-                        const bool is_max = (vhi == mhi) && (vlo == mlo);
-                        const unsigned kmin = __reduce_min_sync(FULL, is_max ? (unsigned)k : 0xffffffffu);
-                        const double vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-                        if (vmax > gb) { gb = vmax; gk = kmin; }      // ascending windows: the earlier sample keeps a tie
+                        if (v > best || (v == best && v > 0.0 && c < kbest)) { best = v; kbest = c; }
+                    };
+                    int c_lo, c_hi;                                                 // candidate range [c_lo, c_hi]
+                    if (qa == qb) {
+                        const int k0 = (int)((W[off + qa] >> 22) & 2047u);
+                        c_lo = max(lo, min(hi - 1, k0 - 1));
+                        c_hi = min(hi - 1, max(lo, k0 + 1));
+                    } else {
+                        float zx = 0.0f, zy = 0.0f, asum = 0.0f;
+#pragma unroll 1
+                        for (int q = off + qa; q <= off + qb; q++) {
+                            const float A = (float)A0[q], sn = (float)A1[q], cs = (float)A3[q];
+                            zx += A * (cs * cs - sn * sn);
+                            zy += A * (2.0f * sn * cs);
+                            asum += A;
+                        }
+                        if (zx * zx + zy * zy < 1e-6f * asum * asum) {
+                            c_lo = lo; c_hi = hi - 1;
+                        } else {
+                            const float r0 = (atan2f(zy, zx) + 3.14159265f) * (ctau_f * 0.15915494f);
+                            const float rc = 0.5f * (float)(lo + hi - 1) * step;
+                            const float rs = r0 + rintf((rc - r0) / ctau_f) * ctau_f;
+                            const int kc = (int)rintf(rs / step);
+                            c_lo = max(lo, min(hi - 1, kc - 2));
+                            c_hi = min(hi - 1, max(lo, kc + 2));
+                            eval(lo);
+                            eval(hi - 1);
+                        }
                     }
-                    if (lane == src && gb > 0.0) update(gb, (int)gk);
+#pragma unroll 1
+                    for (int c = c_lo; c <= c_hi; c++) eval(c);
+                    k = pend;
                 }
-                if (have) advance();
-                __syncwarp();
             }
 
             if (n_pulses > 0) {

@@ -186,8 +186,11 @@ class BatchGather:
                                    for r in range(self.world)])
             self._peer_cnt.append([hc.get_buffer(r, (self.world * self.n_clouds,), torch.int32)
                                    for r in range(self.world)])
-        self._side = torch.cuda.Stream(device=self.device)
-        self._done = [torch.cuda.Event() for _ in range(self.depth)]
+        # one side stream per peer: the world - 1 pushes of a step run on different copy engines at the same time (one
+        # stream serialised them: 8 GPUs, 587 MB out per rank and step took 1.75 ms, i.e. 335 GB/s of the ~770 GB/s a
+        # GPU can send over NVLink)
+        self._side = [torch.cuda.Stream(device=self.device) for _ in range(max(1, self.world))]
+        self._done = [[torch.cuda.Event() for _ in range(max(1, self.world))] for _ in range(self.depth)]
         self._ready = torch.cuda.Event()
 
     def start(self, j, points, counts):
@@ -200,13 +203,14 @@ class BatchGather:
         self._ready.record(cur)
         r0, r1 = self.rank * self.n_rows, (self.rank + 1) * self.n_rows
         c0, c1 = self.rank * self.n_clouds, (self.rank + 1) * self.n_clouds
-        with torch.cuda.stream(self._side):
-            self._side.wait_event(self._ready)
-            for k in range(self.world):                    # start with the right-hand neighbour: spreads the NVSwitch load
-                r = (self.rank + 1 + k) % self.world
+        for k in range(self.world):                        # start with the right-hand neighbour: spreads the NVSwitch load
+            r = (self.rank + 1 + k) % self.world
+            st = self._side[k]
+            with torch.cuda.stream(st):
+                st.wait_event(self._ready)
                 self._peer_pts[j][r][r0:r1].copy_(points, non_blocking=True)
                 self._peer_cnt[j][r][c0:c1].copy_(counts, non_blocking=True)
-            self._done[j].record(self._side)
+                self._done[j][k].record(st)
         self.pending[j] = True
 
     def wait(self, j):
@@ -216,7 +220,9 @@ class BatchGather:
             for wk in self.pending[j]:
                 wk.wait()
         else:
-            torch.cuda.current_stream(self.device).wait_event(self._done[j])
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self._done[j]:
+                cur.wait_event(ev)
         self.pending[j] = None
 
     def wait_all(self):
