@@ -158,7 +158,7 @@ __device__ __forceinline__ float azimuth32(float yf, float xf)
     const float axf = fabsf(xf), ayf = fabsf(yf);
     const float mxf = fmaxf(axf, ayf), mnf = fminf(axf, ayf);
     // zeros, infinities, NaNs, denormal-range ratios: the library handles the special cases
-    if (!(mnf > 0.0f) || !(mxf < 3.0e38f) || !(mnf > mxf * 1e-30f)) return azimuth32_slow(yf, xf);
+    if (!(mnf > 0.0f) || !(mxf < 3.0e38f) || !(mnf > mxf * 1e-30f) || xf != xf || yf != yf) return azimuth32_slow(yf, xf);
     const int i = (int)rintf(__fdividef(mnf, mxf) * 32.0f);
     const double c = (double)i * (1.0 / 32.0), mx = (double)mxf, mn = (double)mnf;
     const double t = fma(-c, mx, mn) / fma(c, mn, mx);
