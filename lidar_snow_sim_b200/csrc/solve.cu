@@ -25,9 +25,9 @@
 //     1230-entry table (host, extended precision) and b = r / (c tau) evaluated once per pulse (one sincospi), so a
 //     sample costs a 16-byte load and six float64 operations instead of a sinpi;
 //   * the sample axis is cut into pieces with a fixed set of active pulses; on a piece the summed waveform is a single
-//     sinusoid, so only the samples around its analytic peak and the piece's ends are evaluated (exactly, in dict order
-//     like the reference's i[k] +=; first maximum wins, np.argmax) -- a handful of samples per piece instead of whole
-//     windows, lane-local, 32 beams in parallel.
+//     sinusoid, so only the three samples around its analytic peak (clipped to the piece) are evaluated -- exactly, in
+//     dict order like the reference's i[k] +=; first maximum wins, np.argmax -- instead of whole windows; the pieces of
+//     all 32 beams are handled one per lane, with uniform code.
 //
 // Beams the arena cannot take (more than SOLVE_LCAP occluders) go to the overflow list and are redone by the
 // round-1 list kernel (snowfall.cu, k_snowfall<SLOW_CAP, MODE_LIST>), which has no such limit below 128.
@@ -41,7 +41,7 @@ constexpr int SOLVE_WARPS = SOLVE_TPB / 32;
 #define LSS_SOLVE_CTAS 6
 #endif
 #ifndef LSS_SOLVE_ARENA
-#define LSS_SOLVE_ARENA 192
+#define LSS_SOLVE_ARENA 160
 #endif
 constexpr int SOLVE_CTAS_PER_SM = LSS_SOLVE_CTAS;
 constexpr int ARENA = LSS_SOLVE_ARENA;                 // slots per warp: sum over the 32 beams of (occluders + 1); more -> extra round
@@ -343,7 +343,11 @@ __device__ __forceinline__ void pulse_phase(double r, double &sb, double &cb)
 __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs a, int *tile_cursor)
 {
     __shared__ double s_arena[SOLVE_WARPS][4][ARENA];
+    __shared__ unsigned long long s_piece[SOLVE_WARPS][2 * ARENA];  // piece descriptors, then the pieces' maxima
+    __shared__ int s_piece_k[SOLVE_WARPS][2 * ARENA];               // ... and where they are
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long *PD = s_piece[wid];
+    int *PK = s_piece_k[wid];
     // slot arrays of this warp.  Phase 1 (hits): A0 = a1, A1 = a2, A2 = planar range.  Claiming: A0 / A1 prefix = union
     // list, A2 / A3 prefix = (range, ratio) of the claiming particles.  Phase 2 (pulses): A0 = amplitude, A1 = sin phase,
     // A3 = cos phase, A2 = packed (first sample, end sample, sample nearest to the peak).
@@ -561,20 +565,24 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             // Only samples inside some pulse window are non-zero.  Pulse ranges ascend, so first and end samples of the
             // windows ascend too and a sweep over them cuts the sample axis into PIECES on which the set of active pulses is
             // a fixed index range [qa, qb].  On a piece the waveform is ONE sinusoid of period c tau (29.96 samples; a piece
-            // is shorter than a window, 31 samples):
+            // is never longer than a window, 31 samples):
             //     sum_q A_q sin^2(pi (R - r_q) / (c tau)) = C - |Z| / 2 * cos(2 pi R / (c tau) - arg Z),   Z = sum_q A_q e^(2 pi i r_q / (c tau))
-            // so its maximum over the piece's samples is at one of the samples around the analytic peak R* (if inside) or at an
-            // end of the piece.  Those few candidates -- not the whole window -- are evaluated exactly, float64, pulses summed in
-            // dict order like the reference's i[k] +=, and the first maximum wins (np.argmax).  R* only SELECTS candidates
-            // (float32 is ample: the grid is 0.1 m); two samples either side absorb the grid's rounding to 0.01 m.  If the
-            // pulses cancel (|Z| tiny: every sample of the piece has the same value up to rounding) the whole piece is evaluated.
-            // A single pulse peaks at its stored sample k0.  Everything is lane-local: 32 beams advance in parallel, where the
-            // round-2a kernel summed whole group windows with all lanes, one group at a time (47 % of its instructions).
+            // so its maximum over the piece's samples is at the sample nearest to the analytic peak R* closest to the piece's
+            // middle -- or, if that lies outside, at the piece's end nearest to it.  The three samples around R*, clipped to
+            // the piece, are evaluated exactly (float64, pulses summed in dict order like the reference's i[k] +=; the first
+            // maximum wins, np.argmax); R* only SELECTS them (float32 is ample: the grid is 0.1 m, its rounding to 0.01 m moves
+            // the nearest sample by at most one).  If the pulses cancel (|Z| tiny: every sample of the piece has the same value
+            // up to rounding) the whole piece is evaluated.  A single pulse peaks at its stored sample k0.
+            //   1. every lane sweeps its own pulses and writes piece descriptors (cheap, divergent);
+            //   2. the pieces of ALL beams of the round are handled one per lane (owner by shuffle binary search): uniform
+            //      code, full warps -- a lane-local version ran at 6 of 32 lanes and the round-2a version summed whole
+            //      windows (47 % of the kernel's instructions);
+            //   3. every lane takes the first maximum over its own pieces.
+            int np_mine = 0;
             if (n_pulses > 0) {
-                const float step = (float)((120 + ctau) / (double)(LSS_M_EXT - 1));
-                const float ctau_f = (float)ctau;
                 int qa = 0, qb = -1, nxt = 0;
                 int k = (int)(W[off] & 2047u);
+                unsigned long long *pd = PD + 2 * off;
 #pragma unroll 1
                 for (;;) {
 #pragma unroll 1
@@ -588,49 +596,85 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                     }
                     int pend = (int)((W[off + qa] >> 11) & 2047u);                 // the oldest active pulse ends first
                     if (nxt < n_pulses) pend = min(pend, (int)(W[off + nxt] & 2047u));
-                    const int lo = k, hi = pend;                                    // piece [lo, hi), active pulses qa .. qb
-                    auto eval = [&](int c) {
-                        const double2 t = __ldg(&a.wtab[c]);
-                        double v = 0.0;
-#pragma unroll 1
-                        for (int q = off + qa; q <= off + qb; q++) {
-                            const double sn = t.x * A3[q] - t.y * A1[q];
-                            v += A0[q] * (sn * sn);
-                        }
-                        if (v > best || (v == best && v > 0.0 && c < kbest)) { best = v; kbest = c; }
-                    };
-                    int c_lo, c_hi;                                                 // candidate range [c_lo, c_hi]
-                    if (qa == qb) {
-                        const int k0 = (int)((W[off + qa] >> 22) & 2047u);
-                        c_lo = max(lo, min(hi - 1, k0 - 1));
-                        c_hi = min(hi - 1, max(lo, k0 + 1));
-                    } else {
-                        float zx = 0.0f, zy = 0.0f, asum = 0.0f;
-#pragma unroll 1
-                        for (int q = off + qa; q <= off + qb; q++) {
-                            const float A = (float)A0[q], sn = (float)A1[q], cs = (float)A3[q];
-                            zx += A * (cs * cs - sn * sn);
-                            zy += A * (2.0f * sn * cs);
-                            asum += A;
-                        }
-                        if (zx * zx + zy * zy < 1e-6f * asum * asum) {
-                            c_lo = lo; c_hi = hi - 1;
-                        } else {
-                            const float r0 = (atan2f(zy, zx) + 3.14159265f) * (ctau_f * 0.15915494f);
-                            const float rc = 0.5f * (float)(lo + hi - 1) * step;
-                            const float rs = r0 + rintf((rc - r0) / ctau_f) * ctau_f;
-                            const int kc = (int)rintf(rs / step);
-                            c_lo = max(lo, min(hi - 1, kc - 2));
-                            c_hi = min(hi - 1, max(lo, kc + 2));
-                            eval(lo);
-                            eval(hi - 1);
-                        }
-                    }
-#pragma unroll 1
-                    for (int c = c_lo; c <= c_hi; c++) eval(c);
+                    // piece [k, pend), active pulses off + qa .. off + qb (at most 2 n_pulses - 1 pieces: they fit 2 (L + 1) slots)
+                    pd[np_mine++] = (unsigned long long)(unsigned)k | ((unsigned long long)(unsigned)pend << 11) |
+                                    ((unsigned long long)(unsigned)(off + qa) << 22) | ((unsigned long long)(unsigned)(off + qb) << 32);
                     k = pend;
                 }
             }
+            int pincl = np_mine;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const int t = __shfl_up_sync(FULL, pincl, sft);
+                if (lane >= sft) pincl += t;
+            }
+            const int pex = pincl - np_mine;
+            const int ptotal = __shfl_sync(FULL, pincl, 31);
+            __syncwarp();
+            {
+                const float step = (float)((120 + ctau) / (double)(LSS_M_EXT - 1));
+                const float ctau_f = (float)ctau;
+#pragma unroll 1
+                for (int f0 = 0; f0 < ptotal; f0 += 32) {
+                    const int f = f0 + lane;
+                    int j = 0;                                      // owner: the last lane whose piece offset is <= f
+#pragma unroll
+                    for (int stp = 16; stp; stp >>= 1) {
+                        const int c = j + stp;
+                        const int oc = __shfl_sync(FULL, pex, c & 31);
+                        if (c < 32 && oc <= f) j = c;
+                    }
+                    const int slot = 2 * __shfl_sync(FULL, off, j) + (f - __shfl_sync(FULL, pex, j));
+                    if (f < ptotal) {
+                        const unsigned long long d = PD[slot];
+                        const int lo = (int)(d & 2047u), hi = (int)((d >> 11) & 2047u);
+                        const int qa = (int)((d >> 22) & 1023u), qb = (int)((d >> 32) & 1023u);
+                        double pbest = 0.0;
+                        int pk = lo;
+                        auto eval = [&](int c) {
+                            const double2 t = __ldg(&a.wtab[c]);
+                            double v = 0.0;
+#pragma unroll 1
+                            for (int q = qa; q <= qb; q++) {
+                                const double sn = t.x * A3[q] - t.y * A1[q];
+                                v += A0[q] * (sn * sn);
+                            }
+                            if (v > pbest) { pbest = v; pk = c; }   // ascending c: the first maximum stays
+                        };
+                        int kc;
+                        bool all = false;
+                        if (qa == qb) {
+                            kc = (int)((W[qa] >> 22) & 2047u);
+                        } else {
+                            float zx = 0.0f, zy = 0.0f, asum = 0.0f;
+#pragma unroll 1
+                            for (int q = qa; q <= qb; q++) {
+                                const float A = (float)A0[q], sn = (float)A1[q], cs = (float)A3[q];
+                                zx += A * (cs * cs - sn * sn);
+                                zy += A * (2.0f * sn * cs);
+                                asum += A;
+                            }
+                            all = zx * zx + zy * zy < 1e-6f * asum * asum;
+                            const float r0 = (atan2f(zy, zx) + 3.14159265f) * (ctau_f * 0.15915494f);
+                            const float rc = 0.5f * (float)(lo + hi - 1) * step;
+                            kc = (int)rintf((r0 + rintf((rc - r0) / ctau_f) * ctau_f) / step);
+                        }
+                        const int c_lo = all ? lo : max(lo, min(hi - 1, kc - 1));
+                        const int c_hi = all ? hi - 1 : min(hi - 1, max(lo, kc + 1));
+#pragma unroll 1
+                        for (int c = c_lo; c <= c_hi; c++) eval(c);
+                        PD[slot] = (unsigned long long)__double_as_longlong(pbest);
+                        PK[slot] = pk;
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int r = 0; r < np_mine; r++) {                     // pieces ascend in sample index: strict > keeps the first maximum
+                const double v = __longlong_as_double((long long)PD[2 * off + r]);
+                if (v > best) { best = v; kbest = PK[2 * off + r]; }
+            }
+            __syncwarp();
 
             if (n_pulses > 0) {
                 // ---- new range / intensity / label (simulation.py:151-188) -------------------------------------------------
