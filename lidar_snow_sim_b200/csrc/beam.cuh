@@ -4,15 +4,15 @@
 #include "common.cuh"
 
 // One beam of the solve list, written by the scan kernel (32 bytes).  The scan has already walked the beam's whole
-// bucket prefix and tested every candidate exactly, so it hands over WHICH prefix entries hit (their positions, in
-// prefix order, in the hit-position array) and the azimuth it used.
+// bucket prefix and tested every candidate exactly, so it hands over WHICH particles hit (their indices, in prefix
+// order, in the hit array) and the azimuth it used.
 struct __align__(16) SolveItem {
     unsigned long long key;       // work class << 48 | cloud << 32 | row
-    int e0;                       // first entry of the beam's azimuth bucket
-    int hit_off;                  // first of the beam's L positions in hit_pos[]
+    int hit_off;                  // first of the beam's L entries of hit_idx[]
     int L;                        // occluders
     float th32;                   // beam azimuth in [0, 2 pi) as the scan used it
-    long long pbase;              // first particle of the beam's plane (entries hold plane-local indices)
+    int pad0;
+    long long pad1;
 };
 
 // argument block of the per-beam kernels (global type: it crosses translation units)
@@ -65,7 +65,7 @@ struct DevArgs {
     const SolveItem *items_in;
     int *hdr;                    // [0] listed beams, [1] overflow beams, [2] tile cursor, [3] hit positions used, class counts ...
     int items_cap;
-    unsigned short *hit_pos;     // prefix positions of the hits of the listed beams
+    int *hit_idx;                // particle indices of the hits of the listed beams
     int hit_cap;
     // optional by-product of the scan kernel for the concurrent pre-pass: the mounting-window points of calculate_plane
     // (tools/wet_ground/planes.py:21-27) compacted per 32-row tile (prepass.cu, PrepassIO::window_staged)

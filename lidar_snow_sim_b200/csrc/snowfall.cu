@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
 // (the warp runs as long as its slowest lane).  hdr: [0] entries, [LIST_CLASSES + c] class counts (from the scan kernel),
 // [2 * LIST_CLASSES + c] class cursors.  Order inside a class is arbitrary: the results do not depend on list order.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int HIT_POS_PER_BEAM = 8;                 // capacity of the hit-position array per beam of the batch
+constexpr int HIT_POS_PER_BEAM = 6;                 // capacity of the hit-position array per beam of the batch
 constexpr int SORT_PER_THREAD = 8;
 __global__ void __launch_bounds__(256) k_list_sort(const SolveItem *__restrict__ in, SolveItem *out, int *hdr, int cap)
 {
@@ -756,10 +756,10 @@ WsLayout ws_layout(int64_t n_total, int n_clouds)
     w.counters_bytes = align_up((int64_t)n_clouds * 2 * 4, 8) + (int64_t)n_clouds * LSS_N_CHANNELS * 4 + (int64_t)n_clouds * 8;
     w.counters = o;   o = align_up(o + w.counters_bytes, 256);
     // list header | overflow list | solve list, unsorted + sorted (every beam may have occluders)
-    //   | hit positions (u16; HIT_POS_PER_BEAM per beam of the batch on average: the surveyed densities give 1-5 occluders
+    //   | hit particle indices (int32; HIT_POS_PER_BEAM per beam of the batch on average: the surveyed densities give 1-5 occluders
     //   on a third of the beams)
     w.ovf = o;        o = align_up(o + LIST_HDR_BYTES + (int64_t)OVF_LIST_CAP * 8 + 2 * n_total * (int64_t)sizeof(SolveItem) +
-                                   (n_total * HIT_POS_PER_BEAM + 4096) * 2, 256);
+                                   (n_total * HIT_POS_PER_BEAM + 4096) * 4, 256);
     w.prepass_bytes = lss_prepass_ws_bytes(n_total, n_clouds);
     w.prepass = o;    o = align_up(o + w.prepass_bytes, 256);
     w.total = o;
@@ -878,7 +878,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
     unsigned long long *d_ovf_list = (unsigned long long *)(ws + w.ovf + LIST_HDR_BYTES);
     SolveItem *d_solve_list = (SolveItem *)(d_ovf_list + OVF_LIST_CAP);
     SolveItem *d_sorted_list = d_solve_list + N;
-    a.hit_pos = (unsigned short *)(d_sorted_list + N);
+    a.hit_idx = (int *)(d_sorted_list + N);
     // Device pre-pass: plane + laser parameters + threshold polynomial (simulation.py:449-467), on the cloud as given.
     // Only k_keep needs its result, so it runs on one of the engine's high-priority side streams next to the beam kernels (a
     // chain of small latency-bound kernels).

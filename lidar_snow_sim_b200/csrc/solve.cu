@@ -104,7 +104,7 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
 __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
 {
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
-    __shared__ unsigned short s_pos[SNOW_WARPS][32][SURV_CAP];     // prefix positions of each lane's survivors
+    __shared__ int s_idx[SNOW_WARPS][32][SURV_CAP];                // plane-local particle index of each lane's survivors
     __shared__ unsigned s_hit[SNOW_WARPS][32];                     // bit r: survivor r of this lane is a hit
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.y, blk0 = blockIdx.x * SNOW_TPB, i = blk0 + threadIdx.x;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
             e1 = bs[1];
             pbase = a.plane_off[plane];
             // ---- phase A: broad phase over the prefix of entries nearer than the target, four loads in flight --------------
-            unsigned short *pos = s_pos[wid][lane];
+            int *pos = s_idx[wid][lane];
             bool stop = false;
 #pragma unroll 1
             for (int e = e0; e < e1 && !stop; e += 4) {
@@ -178,8 +178,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
                     const EntryView en = lss_decode(raw[q], a.zbase);
                     if (!(en.x < d32)) { stop = true; continue; }               // sorted by range: nothing nearer follows
                     if (!(fabsf(en.y - th_rel) <= en.z)) continue;               // float32 broad phase (conservative)
-                    const int t = e + q - e0;
-                    if (ns < SURV_CAP && t < 65536) pos[ns] = (unsigned short)t;
+                    if (ns < SURV_CAP) pos[ns] = en.idx;
                     else slow = true;
                     ns++;
                 }
@@ -209,7 +208,6 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
             if (c < 32 && oc <= s) j = c;
         }
         const int r = s - __shfl_sync(FULL, off, j);
-        const int e0j = __shfl_sync(FULL, e0, j);
         const long long pbj = __shfl_sync(FULL, pbase, j);
         Beam bj;
         bj.d = shfl_f64(bm.d, j);
@@ -217,10 +215,9 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
         bj.left = shfl_f64(bm.left, j);
         bj.straddle = bj.right > bj.left;
         if (s < total) {
-            const BroadEntry raw = __ldg(&a.entries[e0j + s_pos[wid][j][r]]);
             double rho;
             bool rh, lh;
-            if (exact_hit(a.rec + pbj + (raw.y & ((1u << LSS_IDX_BITS) - 1u)), bj, rho, rh, lh)) atomicOr(&s_hit[wid][j], 1u << r);
+            if (exact_hit(a.rec + pbj + s_idx[wid][j][r], bj, rho, rh, lh)) atomicOr(&s_hit[wid][j], 1u << r);
         }
     }
     __syncwarp();
@@ -268,19 +265,19 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
                 if (slot < a.items_cap) {
                     SolveItem it;
                     it.key = ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
-                    it.e0 = e0;
                     it.hit_off = hoff;
                     it.L = fits ? L : 0x7fff;
                     it.th32 = th32;
-                    it.pbase = pbase;
+                    it.pad0 = 0;
+                    it.pad1 = 0;
                     a.items_out[slot] = it;
                 }
                 if (fits) {
-                    unsigned short *hp = a.hit_pos + hoff;
+                    int *hp = a.hit_idx + hoff;                 // particle indices of the hits, in prefix (~ range) order
                     if (!slow) {
-                        const unsigned short *pos = s_pos[wid][lane];
+                        const int *pos = s_idx[wid][lane];
 #pragma unroll 1
-                        for (int k = 0; hits; hits &= hits - 1) hp[k++] = pos[__ffs(hits) - 1];
+                        for (int k = 0; hits; hits &= hits - 1) hp[k++] = (int)pbase + pos[__ffs(hits) - 1];
                     } else {
                         int k = 0;
 #pragma unroll 1
@@ -290,7 +287,7 @@ __global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
                             if (!(fabsf(en.y - th_rel) <= en.z)) continue;
                             double rho;
                             bool rh, lh;
-                            if (exact_hit(a.rec + pbase + en.idx, bm, rho, rh, lh)) hp[k++] = (unsigned short)min(e - e0, 65535);
+                            if (exact_hit(a.rec + pbase + en.idx, bm, rho, rh, lh)) hp[k++] = (int)pbase + en.idx;
                         }
                     }
                 }
@@ -367,7 +364,7 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         const int slot = tile * 32 + lane;
         const bool active = slot < cnt;
         SolveItem it;
-        it.key = 0ull; it.e0 = 0; it.hit_off = 0; it.L = 0; it.th32 = 0.0f; it.pbase = 0;
+        it.key = 0ull; it.hit_off = 0; it.L = 0; it.th32 = 0.0f; it.pad0 = 0; it.pad1 = 0;
         if (active) it = a.items_in[slot];
         const int b = (int)((it.key >> 32) & 0xffffu);
         const int i = (int)(it.key & 0xffffffffu);
@@ -385,7 +382,7 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
         long long att_new_i = -1;
         int n_claim = 0;
 
-        // what the scan kernel found on this beam's bucket prefix: L hits, their prefix positions in hit_pos[hit_off ..]
+        // what the scan kernel found on this beam's bucket prefix: L hits, their particle indices in hit_idx[hit_off ..]
         const int L = active ? it.L : 0;
         Beam bm;
         bm.d = (double)d32;
@@ -432,8 +429,6 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                 const int r = s - __shfl_sync(FULL, off, j);
                 const int Lj = __shfl_sync(FULL, L, j);
                 const int hoj = __shfl_sync(FULL, it.hit_off, j);
-                const int e0j = __shfl_sync(FULL, it.e0, j);
-                const long long pbj = __shfl_sync(FULL, it.pbase, j);
                 const int inr = __shfl_sync(FULL, (int)in_round, j);
                 Beam bj;
                 bj.d = shfl_f64(bm.d, j);
@@ -441,20 +436,13 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                 bj.left = shfl_f64(bm.left, j);
                 bj.straddle = bj.right > bj.left;
                 if (s < total && inr && r < Lj) {                   // (slot L of a beam is its hard target: filled later)
-                    const int t = a.hit_pos[hoj + r];
-                    const BroadEntry raw = __ldg(&a.entries[e0j + t]);
-                    const long long pi = pbj + (raw.y & ((1u << LSS_IDX_BITS) - 1u));
+                    const int pi = a.hit_idx[hoj + r];
+                    const ParticleTan tn = a.tan[pi];               // (both records requested before either is used)
                     double rho;
                     bool rh, lh;
                     exact_hit(a.rec + pi, bj, rho, rh, lh);
-                    double a1 = bj.right, a2 = bj.left;             // geometry.py:26-27: a limit ray the disk crosses clips
-                    if (!rh || !lh) {
-                        const ParticleTan tn = a.tan[pi];
-                        if (!rh) a1 = tn.t_right;
-                        if (!lh) a2 = tn.t_left;
-                    }
-                    A0[s] = a1;
-                    A1[s] = a2;
+                    A0[s] = rh ? bj.right : tn.t_right;             // geometry.py:26-27: a limit ray the disk crosses clips
+                    A1[s] = lh ? bj.left : tn.t_left;
                     A2[s] = rho;
                 }
             }
