@@ -101,7 +101,10 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
     return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
-__global__ void __launch_bounds__(SNOW_TPB, 1024 / SNOW_TPB) k_scan(DevArgs a)
+#ifndef LSS_SCAN_CTAS
+#define LSS_SCAN_CTAS 8
+#endif
+__global__ void __launch_bounds__(SNOW_TPB, LSS_SCAN_CTAS) k_scan(DevArgs a)
 {
     __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
     __shared__ int s_idx[SNOW_WARPS][32][SURV_CAP];                // plane-local particle index of each lane's survivors
