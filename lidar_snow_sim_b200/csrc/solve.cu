@@ -102,7 +102,7 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
 }
 
 #ifndef LSS_SCAN_CTAS
-#define LSS_SCAN_CTAS 8
+#define LSS_SCAN_CTAS 10
 #endif
 __global__ void __launch_bounds__(SNOW_TPB, LSS_SCAN_CTAS) k_scan(DevArgs a)
 {
@@ -481,30 +481,29 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                     ep_min = fmin(ep_min, fmin(lo, hi));
                     ep_max = fmax(ep_max, fmax(lo, hi));
                     if (!(lo < hi)) continue;
+                    // one pass over the union list: is [lo, hi] inside one of its intervals (then nothing is claimed and the list
+                    // stays as it is -- no earlier interval can have overlapped, so nothing has been moved yet), how much of it
+                    // is covered, and the merged list (overlapping / touching intervals absorbed into [nlo, nhi], the others
+                    // compacted in place)
                     bool contained = false;
-                    double cov = 0.0;
-#pragma unroll 1
-                    for (int u = 0; u < nu; u++) {
-                        const double ul = A0[off + u], uh = A1[off + u];
-                        contained |= (ul <= lo) && (hi <= uh);
-                        const double ov = fmin(hi, uh) - fmax(lo, ul);
-                        if (ov > 0.0) cov += ov;
-                    }
-                    if (contained) continue;
-                    const double claimed = (hi - lo) - cov;
-                    claimed_total += claimed;
-                    double nlo = lo, nhi = hi;      // merge [lo, hi] into the union (absorb overlapping / touching pieces)
+                    double cov = 0.0, nlo = lo, nhi = hi;
                     int w = 0;
 #pragma unroll 1
                     for (int u = 0; u < nu; u++) {
                         const double ul = A0[off + u], uh = A1[off + u];
+                        if ((ul <= lo) && (hi <= uh)) { contained = true; break; }
                         if (ul <= hi && uh >= lo) {
+                            const double ov = fmin(hi, uh) - fmax(lo, ul);
+                            if (ov > 0.0) cov += ov;
                             nlo = fmin(nlo, ul);
                             nhi = fmax(nhi, uh);
                         } else {
                             A0[off + w] = ul; A1[off + w] = uh; w++;
                         }
                     }
+                    if (contained) continue;
+                    const double claimed = (hi - lo) - cov;
+                    claimed_total += claimed;
                     A0[off + w] = nlo; A1[off + w] = nhi;       // w <= nu <= P <= j: only slots of processed hits
                     nu = w + 1;
                     double ratio = claimed / a.div_rad;
