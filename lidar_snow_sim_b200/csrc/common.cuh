@@ -321,3 +321,5 @@ lss_status lss_prepass_run(lss_engine *e, const float *d_pts, const int64_t *d_c
                            int range64, int raise_few_ground, const PrepassIO &io, void *d_ws, int64_t ws_bytes,
                            void **cloudpre_out, cudaStream_t stream);
 int64_t lss_snowfall_ws_bytes(int64_t n_total, int n_clouds);
+// byte offset, inside the snowfall workspace, of the device copy of the cloud offsets (int64[n_clouds + 1]) a call uploads
+int64_t lss_snowfall_ws_cloud_off(int64_t n_total, int n_clouds);

@@ -48,6 +48,30 @@ struct lss_host_pipe {
     int last_slot = -1;                     // slot of the most recently completed batch (lss_host_pipe_trace)
 };
 
+// Copy-out of a chunk's KEPT rows straight into the caller's page-locked host buffer (zero-copy stores over PCIe): cloud b
+// occupies rows [off[b], off[b] + count[b]) of its slot, and only those travel -- a cudaMemcpyAsync has to move the whole
+// slot because the counts live on the device (the threshold filter drops 20-35 % of the rows).  Rows are float32 x 5; a
+// cloud's kept rows are contiguous, so consecutive threads write consecutive 4-byte words: fully coalesced PCIe writes.
+// Grid (blocks, clouds of the chunk).
+static __global__ void __launch_bounds__(256) k_copy_rows_out(const float *__restrict__ d_out, const int64_t *__restrict__ d_off,
+                                                              const int32_t *__restrict__ d_counts, float *h_out)
+{
+    const int b = blockIdx.y;
+    const int64_t beg = d_off[b] * 5, n = (int64_t)d_counts[b] * 5;
+    const float *src = d_out + beg;
+    float *dst = h_out + beg;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // float4 body where both pointers are 16-byte aligned (a cloud starts at a multiple of 5 floats, not of 4)
+    const int64_t mis_d = (int64_t)(((uintptr_t)dst >> 2) & 3), mis_s = (int64_t)(((uintptr_t)src >> 2) & 3);
+    const int64_t head = mis_d == mis_s ? ((4 - mis_d) & 3) : n;       // differently aligned: everything word by word
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < head && i < n; i += stride) dst[i] = src[i];
+    const int64_t n4 = n > head ? (n - head) / 4 : 0;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src + head);
+    float4 *d4 = reinterpret_cast<float4 *>(dst + head);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) d4[i] = s4[i];
+    for (int64_t i = head + 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
 static void pipe_quiesce(lss_host_pipe *p)
 {
     if (p->s_h2d) cudaStreamSynchronize(p->s_h2d);
@@ -183,6 +207,18 @@ extern "C" lss_status lss_snowfall_batch_host_submit(lss_engine *e, int table_id
     lss_status rc = LSS_OK;
     cudaError_t ce = cudaSuccess;
     std::vector<int64_t> loc_off;
+    // Is the result buffer page-locked (and therefore addressable from the device)?  Then the copy-out is a kernel that
+    // writes only the kept rows; pageable memory gets the plain full-slot cudaMemcpyAsync.  LSS_PIPE_DMA_OUT=1 forces the latter.
+    float *h_out_dev = nullptr;
+    {
+        static const bool force_dma = getenv("LSS_PIPE_DMA_OUT") && getenv("LSS_PIPE_DMA_OUT")[0] == '1';
+        cudaPointerAttributes pa;
+        if (!force_dma && cudaPointerGetAttributes(&pa, h_out_points) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+            pa.devicePointer != nullptr)
+            h_out_dev = (float *)pa.devicePointer;
+        cudaGetLastError();
+    }
+    constexpr int COPY_OUT_BLOCKS = 8;
     int *const engine_status = e->d_status;
     e->d_status = sl.d_status;                       // the kernels of this batch latch their errors per slot
     {
@@ -234,9 +270,19 @@ extern "C" lss_status lss_snowfall_batch_host_submit(lss_engine *e, int table_id
         if (rc != LSS_OK) break;
         ce = cudaEventRecord(ev_beam, sb);
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(p->s_d2h, ev_beam, 0);
-        if (ce == cudaSuccess && nr > 0)
-            ce = cudaMemcpyAsync(h_out_points + r0 * 5, sl.d_out + r0 * 5, (size_t)nr * 5 * sizeof(float),
-                                 cudaMemcpyDeviceToHost, p->s_d2h);
+        if (ce == cudaSuccess && nr > 0) {
+            if (h_out_dev) {        // page-locked result buffer: only the kept rows travel (see k_copy_rows_out)
+                // cloud offsets of this chunk on the device: the snowfall stage uploaded them to the head of its workspace
+                const int64_t *d_off_chunk = (const int64_t *)(ws + lss_snowfall_ws_cloud_off(nr, nb));
+                k_copy_rows_out<<<dim3(COPY_OUT_BLOCKS, nb), 256, 0, p->s_d2h>>>(sl.d_out + r0 * 5, d_off_chunk, sl.d_counts + b0,
+                                                                               h_out_dev + r0 * 5);
+                e->launches++;
+                ce = cudaGetLastError();
+            } else {
+                ce = cudaMemcpyAsync(h_out_points + r0 * 5, sl.d_out + r0 * 5, (size_t)nr * 5 * sizeof(float),
+                                     cudaMemcpyDeviceToHost, p->s_d2h);
+            }
+        }
         if (ce == cudaSuccess)
             ce = cudaMemcpyAsync(h_out_counts + b0, sl.d_counts + b0, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, p->s_d2h);
         if (ce == cudaSuccess)

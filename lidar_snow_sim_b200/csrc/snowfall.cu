@@ -774,6 +774,8 @@ int64_t lss_snowfall_ws_bytes(int64_t n_total, int n_clouds)
     return ws_layout(n_total, n_clouds).total;
 }
 
+int64_t lss_snowfall_ws_cloud_off(int64_t n_total, int n_clouds) { return ws_layout(n_total, n_clouds).cloud_off; }
+
 lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t stream)
 {
     const int B = s.n_clouds;
