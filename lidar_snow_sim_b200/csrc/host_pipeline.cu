@@ -207,13 +207,15 @@ extern "C" lss_status lss_snowfall_batch_host_submit(lss_engine *e, int table_id
     lss_status rc = LSS_OK;
     cudaError_t ce = cudaSuccess;
     std::vector<int64_t> loc_off;
-    // Is the result buffer page-locked (and therefore addressable from the device)?  Then the copy-out is a kernel that
-    // writes only the kept rows; pageable memory gets the plain full-slot cudaMemcpyAsync.  LSS_PIPE_DMA_OUT=1 forces the latter.
+    // Copy-out: by default a cudaMemcpyAsync of the whole slot on the copy engine.  LSS_PIPE_KERNEL_OUT=1 (and a page-locked
+    // result buffer, i.e. one the device can address) selects k_copy_rows_out, which moves only the kept rows: measured on one
+    // B200 it does NOT pay (2.12 vs 2.06 ms per step: SM-issued PCIe writes are slower than the copy engine by more than
+    // the 25 % of bytes saved); it is kept for hosts whose memory write bandwidth is the limiter (8 ranks on one box).
     float *h_out_dev = nullptr;
     {
-        static const bool force_dma = getenv("LSS_PIPE_DMA_OUT") && getenv("LSS_PIPE_DMA_OUT")[0] == '1';
+        static const bool kernel_out = getenv("LSS_PIPE_KERNEL_OUT") && getenv("LSS_PIPE_KERNEL_OUT")[0] == '1';
         cudaPointerAttributes pa;
-        if (!force_dma && cudaPointerGetAttributes(&pa, h_out_points) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+        if (kernel_out && cudaPointerGetAttributes(&pa, h_out_points) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
             pa.devicePointer != nullptr)
             h_out_dev = (float *)pa.devicePointer;
         cudaGetLastError();

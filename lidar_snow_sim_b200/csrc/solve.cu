@@ -571,21 +571,29 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             int np_mine = 0;
             if (n_pulses > 0) {
                 int qa = 0, qb = -1, nxt = 0;
-                int k = (int)(W[off] & 2047u);
+                int ks_n = (int)(W[off] & 2047u);                   // first sample of the next pulse to start (cached)
+                int ke_a = 0;                                       // end sample of the oldest active pulse (cached)
+                int k = ks_n;
                 unsigned long long *pd = PD + 2 * off;
 #pragma unroll 1
                 for (;;) {
 #pragma unroll 1
-                    while (nxt < n_pulses && (int)(W[off + nxt] & 2047u) <= k) { qb = nxt; nxt++; }
+                    while (ks_n <= k) {
+                        qb = nxt++;
+                        ks_n = nxt < n_pulses ? (int)(W[off + nxt] & 2047u) : 4096;
+                    }
 #pragma unroll 1
-                    while (qa <= qb && (int)((W[off + qa] >> 11) & 2047u) <= k) qa++;
+                    while (qa <= qb) {
+                        ke_a = (int)((W[off + qa] >> 11) & 2047u);
+                        if (ke_a > k) break;
+                        qa++;
+                    }
                     if (qa > qb) {
                         if (nxt >= n_pulses) break;
-                        k = (int)(W[off + nxt] & 2047u);
+                        k = ks_n;
                         continue;
                     }
-                    int pend = (int)((W[off + qa] >> 11) & 2047u);                 // the oldest active pulse ends first
-                    if (nxt < n_pulses) pend = min(pend, (int)(W[off + nxt] & 2047u));
+                    const int pend = min(ke_a, ks_n);               // the oldest active pulse ends first, or the next one starts
                     // piece [k, pend), active pulses off + qa .. off + qb (at most 2 n_pulses - 1 pieces: they fit 2 (L + 1) slots)
                     pd[np_mine++] = (unsigned long long)(unsigned)k | ((unsigned long long)(unsigned)pend << 11) |
                                     ((unsigned long long)(unsigned)(off + qa) << 22) | ((unsigned long long)(unsigned)(off + qb) << 32);
