@@ -3,8 +3,8 @@
 //   k_scan   every beam of the batch, one thread per beam, rows in INPUT order: float32 range / azimuth, walk of the
 //            beam's azimuth bucket of its channel's snowflake plane (float32 broad phase, exact float64 disk / wedge test)
 //            over the WHOLE prefix of entries nearer than the target.  Beams without occluder (~2/3) are finished here;
-//            the others are pushed to the solve list together with what the walk found: the bit mask of the prefix
-//            positions that hit, the bucket, the azimuth.                    (tools/snowfall/simulation.py:80-101, 329-390)
+//            the others are pushed to the solve list together with what the walk found: the particle indices of the
+//            hits (in prefix order) and the azimuth.                         (tools/snowfall/simulation.py:80-101, 329-390)
 //   k_solve  the listed beams, sorted by work class: tangent angles of the hits, nearest-first claiming of the beam's
 //            angular sub-intervals, summed sin^2 waveform + argmax, relabel / move the point, label-1 statistics.
 //                                                                              (simulation.py:118-188, 231-295, 391-424)
@@ -17,8 +17,8 @@
 //   * NO local memory: the beams of a warp share a shared-memory arena of ARENA slots, allocated exactly
 //     (occluders + 1 per beam) with a warp scan of the counts the scan kernel delivered;
 //   * the hits are loaded COOPERATIVELY: arena slot s is filled by lane s mod 32, whatever beam it belongs to (owner by
-//     a shuffle binary search over the offsets, the slot's prefix position = the r-th set bit of the owner's mask), so
-//     the dependent entry -> record loads of all beams are in flight together; the owner then orders its few slots by range;
+//     a shuffle binary search over the offsets, the slot's particle = the r-th hit index the scan stored for the owner),
+//     so the index -> record loads of all beams are in flight together; the owner then orders its few slots by range;
 //   * nearest-first claiming runs in place in the arena: the union list lives in the slots of the already processed
 //     hits, pulses (range, ratio) are compacted to the front;
 //   * waveform: sin(pi (R_k - r) / (c tau)) = sin(pi a_k) cos(pi b) - cos(pi a_k) sin(pi b) with a_k = R_k / (c tau) from a
@@ -86,8 +86,8 @@ __device__ __forceinline__ bool exact_hit(const ParticleRec *rp, const Beam &bm,
 // Two phases per warp (32 consecutive rows), because a thread-per-beam loop that tests a candidate exactly as soon as it
 // finds one pays the latency of that dependent record load in EVERY iteration in which any lane of the warp has a
 // candidate (measured: the exact tests ran at 5 of 32 lanes and dominated the kernel):
-//   A  each lane walks its beam's bucket prefix with the float32 broad phase only -- a streaming read of 16-byte
-//      entries, four loads in flight -- and notes the positions of the survivors (shared memory, SURV_CAP per lane);
+//   A  each lane walks its beam's bucket prefix with the float32 broad phase only -- a streaming read of 8-byte
+//      entries, four loads in flight -- and notes the particle indices of the survivors (shared memory, SURV_CAP per lane);
 //   B  the survivors of all 32 beams are tested exactly by ALL lanes, one survivor per lane and round (owner by a
 //      shuffle binary search), so the record loads of the whole warp are in flight together; hits are flagged in a
 //      per-beam bit mask.
