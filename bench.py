@@ -359,7 +359,7 @@ def main():
     gather = None
     if do_gather:
         from lidar_snow_sim_b200.distributed import BatchGather
-        gather = BatchGather(N, B, dev, depth=2)
+        gather = BatchGather(N, B, dev, depth=2, engine=eng, cloud_offsets=off)
 
     # config 2: the wet stage of step k runs on its own stream next to the snow stage of step k + 1 (both are chains of
     # latency-bound kernels; the wet pre-pass can only start when the snow output exists).  Double-buffered, stream-ordered.
@@ -627,6 +627,7 @@ def main():
             'engine': {'prepass': 'device' if device_prepass else 'DEBUG: fixed host-supplied threshold polynomial',
                        'table_particles': tinfo['n_particles'], 'table_index_bytes': tinfo['bytes'],
                        'gather': None if gather is None else gather.kind,
+                       'gather_multicast': None if gather is None else getattr(gather, 'multicast', False),
                        'gather_fallback': None if gather is None else getattr(gather, 'fallback_reason', None)}}
     print(json.dumps(line))
     if world > 1:

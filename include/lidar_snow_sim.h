@@ -296,6 +296,26 @@ LSS_API lss_status lss_voxelize_batch(lss_engine *e, const float *d_points, int 
                                       int64_t workspace_bytes, void *stream);
 LSS_API int64_t lss_voxelize_workspace_bytes(int64_t n_total, int n_clouds, int max_points_per_voxel, int max_voxels);
 
+/* ---- exchange step of the sharded batch (BASELINE.json configs[3]) ------------------------------------------
+ * The reference has no multi-GPU augmentation; its collectives are OpenPCDet's result merging
+ * (lib/OpenPCDet/pcdet/utils/commu_utils.py:77,90: all_gather of pickled, variable-size objects).  The sharded engine
+ * reassembles the augmented batch on every rank instead: gathered row buffer float32[world * n_rows * 5] (rank r's
+ * slot-compacted batch at rows [r * n_rows, (r + 1) * n_rows)) and gathered counts int32[world * n_clouds].
+ * lss_gather_push writes the KEPT rows of this rank's batch (cloud b: rows [off[b], off[b] + count[b])) and its counts into
+ * every rank's gathered buffers with peer-to-peer stores over NVLink -- one small kernel (CTAs of 128 threads x 32 registers,
+ * which fit next to the persistent solve kernel of the following step), no library collective, no whole-slot copy.
+ *   d_points / d_counts / d_cloud_offsets   this rank's output of lss_snowfall_batch (counts may be NULL: all rows), offsets on
+ *                       the DEVICE (int64[n_clouds + 1])
+ *   h_peer_points[world], h_peer_counts[world]   host arrays of DEVICE pointers: every rank's gathered buffers as mapped into
+ *                       this process (peer mappings of a symmetric allocation; entry `rank` is the local buffer)
+ *   d_mc_points / d_mc_counts   multicast (NVLS) mappings of the same allocations, or both NULL: then one store per peer
+ *   n_blocks            CTAs to launch (<= 0: one per SM, a quarter of that with multicast)
+ * Stream-ordered on `stream`; a consumer on ANOTHER rank needs a barrier across ranks after this rank's kernel has finished. */
+LSS_API lss_status lss_gather_push(lss_engine *e, const float *d_points, const int32_t *d_counts,
+                                   const int64_t *d_cloud_offsets, int n_clouds, int64_t n_rows, int world, int rank,
+                                   float *const *h_peer_points, int32_t *const *h_peer_counts, float *d_mc_points,
+                                   int32_t *d_mc_counts, int n_blocks, void *stream);
+
 /* ---- snowflake table sampler ---------------------------------------------------------------------------------------
  * dart_throwing(occupancy_ratio, precipitation_rate, R_0, rng, distribution) of tools/snowfall/sampling.py:90-194:
  * sequential rejection sampling of non-overlapping disks in a disk of radius R_0 until the occupied area reaches

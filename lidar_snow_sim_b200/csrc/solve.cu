@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             const int off = incl - mine;                            // exclusive offsets: non-decreasing over the lanes
             const int total = (int)__reduce_max_sync(FULL, in_round ? (unsigned)incl : 0u);
             int n_pulses = 0;
+            double amax = 0.0;                                      // largest pulse amplitude of this beam (prunes the pieces)
             double best = 0.0;
             int kbest = 0;
 
@@ -530,7 +531,9 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                         bad |= (ke > LSS_M_EXT) || (ks < 0);
                         double sb, cb;
                         pulse_phase(r, sb, cb);
-                        A0[off + j] = (A * ratio * xsi64(r)) / (r * r);
+                        const double amp = (A * ratio * xsi64(r)) / (r * r);
+                        amax = fmax(amax, amp);
+                        A0[off + j] = amp;
                         A1[off + j] = sb;
                         A3[off + j] = cb;
                         W[off + j] = pack_win(ks, ke, (int)rint((r + ctau / 2) * inv_step));
@@ -541,7 +544,9 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
                         bad |= (ke > LSS_M_EXT) || (ks < 0);
                         double sb, cb;
                         pulse_phase(bm.d, sb, cb);
-                        A0[off + P] = (A * ratio_hard * xsi32(d32)) / (double)__fmul_rn(d32, d32);
+                        const double amp = (A * ratio_hard * xsi32(d32)) / (double)__fmul_rn(d32, d32);
+                        amax = fmax(amax, amp);
+                        A0[off + P] = amp;
                         A1[off + P] = sb;
                         A3[off + P] = cb;
                         W[off + P] = pack_win(ks, ke, (int)rint((bm.d + ctau / 2) * inv_step));
@@ -570,6 +575,12 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
             //   3. every lane takes the first maximum over its own pieces.
             int np_mine = 0;
             if (n_pulses > 0) {
+                // Pruning: the largest pulse alone contributes A_max sin^2 >= 0.9966 A_max at its stored peak sample (at most
+                // half a grid step + the grid's 0.005 m rounding away from r + c tau / 2), every term of the sum is >= 0 and
+                // float64 addition of non-negative terms is monotone, so the waveform's maximum is >= 0.99 A_max.  A piece whose
+                // active amplitudes sum to less than that (sin^2 <= 1) cannot hold the argmax and is not even written down.
+                const double lb = 0.99 * amax;
+                double asum = 0.0;                                  // running sum of the active amplitudes (drift << the margin)
                 int qa = 0, qb = -1, nxt = 0;
                 int ks_n = (int)(W[off] & 2047u);                   // first sample of the next pulse to start (cached)
                 int ke_a = 0;                                       // end sample of the oldest active pulse (cached)
@@ -580,23 +591,27 @@ __global__ void __launch_bounds__(SOLVE_TPB, SOLVE_CTAS_PER_SM) k_solve(DevArgs 
 #pragma unroll 1
                     while (ks_n <= k) {
                         qb = nxt++;
+                        asum += A0[off + qb];
                         ks_n = nxt < n_pulses ? (int)(W[off + nxt] & 2047u) : 4096;
                     }
 #pragma unroll 1
                     while (qa <= qb) {
                         ke_a = (int)((W[off + qa] >> 11) & 2047u);
                         if (ke_a > k) break;
+                        asum -= A0[off + qa];
                         qa++;
                     }
                     if (qa > qb) {
+                        asum = 0.0;
                         if (nxt >= n_pulses) break;
                         k = ks_n;
                         continue;
                     }
                     const int pend = min(ke_a, ks_n);               // the oldest active pulse ends first, or the next one starts
                     // piece [k, pend), active pulses off + qa .. off + qb (at most 2 n_pulses - 1 pieces: they fit 2 (L + 1) slots)
-                    pd[np_mine++] = (unsigned long long)(unsigned)k | ((unsigned long long)(unsigned)pend << 11) |
-                                    ((unsigned long long)(unsigned)(off + qa) << 22) | ((unsigned long long)(unsigned)(off + qb) << 32);
+                    if (asum * 1.0001 >= lb)
+                        pd[np_mine++] = (unsigned long long)(unsigned)k | ((unsigned long long)(unsigned)pend << 11) |
+                                        ((unsigned long long)(unsigned)(off + qa) << 22) | ((unsigned long long)(unsigned)(off + qb) << 32);
                     k = pend;
                 }
             }

@@ -137,34 +137,47 @@ class BatchGather:
     augmented batch ((n_rows, 5) float32, slot-compacted) + per-cloud counts, double-buffered so that the exchange of
     step k overlaps the kernels of step k + 1.
 
-    kind 'ce'   (default when torch's symmetric memory is usable): the gathered buffers are symmetric allocations; each
-                rank PUSHES its slot into every peer's buffer with peer-to-peer device copies on a side stream.  Large
-                device-to-device copies run on the copy engines over NVLink, so no SM is taken from the (latency-bound)
-                beam kernels -- the SM-resident channels of ncclAllGather slowed them by up to 20 % at 8 GPUs (round 1).
-    kind 'nccl' dist.all_gather_into_tensor(async_op=True) on NCCL's stream (also what the gloo CPU tests exercise).
+    kind 'push' (default with an engine and usable symmetric memory): the gathered buffers are symmetric allocations; each
+                rank writes the KEPT rows of its batch into every rank's buffer with the engine's own kernel
+                (lss_gather_push, csrc/gather.cu: peer-to-peer stores over NVLink, or one multicast store per 16 bytes
+                when the allocation has an NVLS mapping) on a high-priority side stream.  Needs `cloud_offsets`.
+    kind 'ce'   the same buffers, whole slots pushed with peer-to-peer device copies (copy engines, no SM): 8 GPUs reached
+                335 GB/s per rank on one stream and less on one stream per peer (profiles/r02_n8*_bench_ce.json).
+    kind 'nccl' dist.all_gather_into_tensor(async_op=True) on NCCL's stream (also what the gloo CPU tests exercise); its
+                SM-resident channels slowed the latency-bound beam kernels by up to 20 % at 8 GPUs (round 1).
 
     Completion: `wait(j)` makes the caller's stream wait for THIS rank's outgoing copies of buffer j; a consumer that
     reads a gathered buffer needs a barrier across ranks first (bench.py brackets end with one).  LSS_GATHER=nccl|ce
     overrides the choice.
     """
 
-    def __init__(self, n_rows, n_clouds, device, depth=2, group=None, kind=None):
+    def __init__(self, n_rows, n_clouds, device, depth=2, group=None, kind=None, engine=None, cloud_offsets=None):
         import os
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.n_rows, self.n_clouds, self.depth = int(n_rows), int(n_clouds), depth
         self.device = device
-        kind = kind or os.environ.get('LSS_GATHER') or ('ce' if getattr(device, 'type', 'cpu') == 'cuda' else 'nccl')
+        on_gpu = getattr(device, 'type', 'cpu') == 'cuda'
+        can_push = on_gpu and engine is not None and cloud_offsets is not None
+        kind = kind or os.environ.get('LSS_GATHER') or ('push' if can_push else ('ce' if on_gpu else 'nccl'))
+        if kind == 'push' and not can_push:
+            kind = 'ce'
         self.pending = [None] * depth
         self.kind = 'nccl'
         self.points = self.counts = None
-        if kind == 'ce':
+        self.engine = engine
+        self.fallback_reason = None
+        self.multicast = False
+        if kind in ('ce', 'push'):
             try:
                 self._init_ce()
-                self.kind = 'ce'
+                self.kind = kind
+                if kind == 'push':
+                    self._init_push(cloud_offsets)
             except Exception as exc:                      # symmetric memory unavailable: fall back, say so
                 self.fallback_reason = f'{type(exc).__name__}: {exc}'
+                self.kind = 'nccl'
         if self.kind == 'nccl':
             self.points = [torch.empty((self.world * self.n_rows, 5), dtype=torch.float32, device=device)
                            for _ in range(depth)]
@@ -174,7 +187,7 @@ class BatchGather:
     def _init_ce(self):
         import torch.distributed._symmetric_memory as symm_mem
         grp = self.group if self.group is not None else dist.group.WORLD
-        self.points, self.counts, self._peer_pts, self._peer_cnt = [], [], [], []
+        self.points, self.counts, self._peer_pts, self._peer_cnt, self._mc = [], [], [], [], []
         for _ in range(self.depth):
             p = symm_mem.empty((self.world * self.n_rows, 5), dtype=torch.float32, device=self.device)
             c = symm_mem.empty((self.world * self.n_clouds,), dtype=torch.int32, device=self.device)
@@ -186,6 +199,7 @@ class BatchGather:
                                    for r in range(self.world)])
             self._peer_cnt.append([hc.get_buffer(r, (self.world * self.n_clouds,), torch.int32)
                                    for r in range(self.world)])
+            self._mc.append((int(getattr(hp, 'multicast_ptr', 0) or 0), int(getattr(hc, 'multicast_ptr', 0) or 0)))
         # one side stream per peer: the world - 1 pushes of a step run on different copy engines at the same time (one
         # stream serialised them: 8 GPUs, 587 MB out per rank and step took 1.75 ms, i.e. 335 GB/s of the ~770 GB/s a
         # GPU can send over NVLink)
@@ -193,8 +207,46 @@ class BatchGather:
         self._done = [[torch.cuda.Event() for _ in range(max(1, self.world))] for _ in range(self.depth)]
         self._ready = torch.cuda.Event()
 
+    def _init_push(self, cloud_offsets):
+        import ctypes
+        import os
+        import numpy as np
+        off = np.ascontiguousarray(cloud_offsets, dtype=np.int64)
+        assert off.shape[0] == self.n_clouds + 1 and int(off[-1]) == self.n_rows
+        self._d_off = torch.from_numpy(off).to(self.device)
+        P = ctypes.c_void_p * self.world
+        self._pp = [P(*[t.data_ptr() for t in self._peer_pts[j]]) for j in range(self.depth)]
+        self._pc = [P(*[t.data_ptr() for t in self._peer_cnt[j]]) for j in range(self.depth)]
+        use_mc = os.environ.get('LSS_GATHER_MULTICAST', '1') != '0'
+        self.multicast = bool(use_mc and all(m[0] and m[1] for m in self._mc))
+        self.blocks = int(os.environ.get('LSS_GATHER_BLOCKS', '0'))
+        try:
+            hi = torch.cuda.Stream.priority_range()[1]     # (least, greatest) = (0, -1) on current GPUs
+        except Exception:
+            hi = -1
+        self._push_stream = torch.cuda.Stream(device=self.device, priority=hi)
+        self._push_done = [torch.cuda.Event() for _ in range(self.depth)]
+
+    def _start_push(self, j, points, counts):
+        from . import _lib
+        eng = self.engine
+        cur = torch.cuda.current_stream(self.device)
+        self._ready.record(cur)
+        st = self._push_stream
+        mcp, mcc = self._mc[j] if self.multicast else (0, 0)
+        with torch.cuda.stream(st):
+            st.wait_event(self._ready)
+            rc = eng.lib.lss_gather_push(eng.h, points.data_ptr(), counts.data_ptr(), self._d_off.data_ptr(), self.n_clouds,
+                                         self.n_rows, self.world, self.rank, self._pp[j], self._pc[j], mcp or None, mcc or None,
+                                         self.blocks, st.cuda_stream)
+            _lib.check(rc, eng.h)
+            self._push_done[j].record(st)
+        self.pending[j] = (points, counts)                 # the kernel reads them: keep them alive until wait(j)
+
     def start(self, j, points, counts):
         """Enqueue the exchange of this rank's (points, counts) into buffer j of every rank."""
+        if self.kind == 'push':
+            return self._start_push(j, points, counts)
         if self.kind == 'nccl':
             self.pending[j] = [dist.all_gather_into_tensor(self.points[j], points, group=self.group, async_op=True),
                                dist.all_gather_into_tensor(self.counts[j], counts, group=self.group, async_op=True)]
@@ -219,6 +271,8 @@ class BatchGather:
         if self.kind == 'nccl':
             for wk in self.pending[j]:
                 wk.wait()
+        elif self.kind == 'push':
+            torch.cuda.current_stream(self.device).wait_event(self._push_done[j])
         else:
             cur = torch.cuda.current_stream(self.device)
             for ev in self._done[j]:

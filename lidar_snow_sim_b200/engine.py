@@ -407,6 +407,23 @@ class SnowfallEngine:
         _lib.check(st, self.h)
         return out
 
+    def gather_push(self, points, counts, d_cloud_offsets, n_rows, world, rank, peer_points, peer_counts, mc_points=0,
+                    mc_counts=0, blocks=0):
+        """lss_gather_push on the current stream: write the kept rows of this rank's slot-compacted batch (+ counts) into
+        every rank's gathered buffers.  peer_points / peer_counts: per rank, a CUDA tensor mapping that
+        rank's gathered buffer (world * n_rows, 5) float32 / (world * n_clouds,) int32 into this process (see
+        distributed.BatchGather, which owns the symmetric allocations and the side stream)."""
+        B = int(d_cloud_offsets.shape[0]) - 1
+        assert points.is_cuda and points.dtype == torch.float32 and points.is_contiguous()
+        assert d_cloud_offsets.is_cuda and d_cloud_offsets.dtype == torch.int64
+        P = ctypes.c_void_p * int(world)
+        pp = P(*[t.data_ptr() for t in peer_points])
+        pc = P(*[t.data_ptr() for t in peer_counts])
+        with torch.cuda.device(self.device):
+            st = self.lib.lss_gather_push(self.h, _ptr(points), _ptr(counts), _ptr(d_cloud_offsets), B, int(n_rows), int(world),
+                                          int(rank), pp, pc, mc_points or None, mc_counts or None, int(blocks), self._stream())
+        _lib.check(st, self.h)
+
     def check(self):
         """Synchronise the current stream and raise the exception type the reference would have raised."""
         with torch.cuda.device(self.device):

@@ -507,3 +507,36 @@ def test_device_azimuth_is_the_rounded_float64_atan2(engine):
         want = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32)
     same = (got.view(np.int32) == want.view(np.int32)) | (np.isnan(got) & np.isnan(want))
     assert same.all(), (int((~same).sum()), x[~same][:5], y[~same][:5], got[~same][:5], want[~same][:5])
+
+
+@pytest.mark.gpu
+def test_gather_push_writes_kept_rows_into_every_peer_buffer(engine):
+    """lss_gather_push on one GPU: the 'peers' are three separate buffers of the same device.  Ragged clouds
+    whose offsets are not multiples of four rows (16-byte misalignment), counts below the slot sizes, an empty cloud."""
+    eng = engine
+    dev = eng.device
+    rng = np.random.default_rng(5)
+    sizes = [1000, 0, 37, 4099, 2, 513]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n_rows, B, world = int(off[-1]), len(sizes), 3
+    counts = np.array([rng.integers(0, s + 1) for s in sizes], dtype=np.int32)
+    counts[3] = sizes[3]
+    pts = torch.from_numpy(rng.normal(size=(n_rows, 5)).astype(np.float32)).to(dev)
+    d_counts = torch.from_numpy(counts).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    for rank in range(world):
+        for use_counts in (True, False):
+            peers = [torch.full((world * n_rows, 5), -7.0, dtype=torch.float32, device=dev) for _ in range(world)]
+            pcnt = [torch.full((world * B,), -7, dtype=torch.int32, device=dev) for _ in range(world)]
+            eng.gather_push(pts, d_counts if use_counts else None, d_off, n_rows, world, rank, peers, pcnt, blocks=3 + rank)
+            torch.cuda.synchronize(dev)
+            want = np.full((world * n_rows, 5), -7.0, dtype=np.float32)
+            wcnt = np.full((world * B,), -7, dtype=np.int32)
+            src = pts.cpu().numpy()
+            for b in range(B):
+                c = int(counts[b]) if use_counts else sizes[b]
+                want[rank * n_rows + off[b]: rank * n_rows + off[b] + c] = src[off[b]: off[b] + c]
+                wcnt[rank * B + b] = c
+            for p in range(world):
+                assert np.array_equal(peers[p].cpu().numpy(), want)
+                assert np.array_equal(pcnt[p].cpu().numpy(), wcnt)

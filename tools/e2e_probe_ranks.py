@@ -28,6 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--bind', type=int, default=1)
     ap.add_argument('--engine', type=int, default=1)
+    ap.add_argument('--trace', type=int, default=0, help='device timeline of synchronous host calls on every rank')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -120,6 +121,28 @@ def main():
                 res[f'pipeline_inflight{depth}_ms'] = [float(x.item()) for x in g]
             else:
                 res[f'pipeline_inflight{depth}_ms'] = [dt]
+        if args.trace:
+            # where does a synchronous call spend its time when all ranks run at once?  Device timeline of the last of 6
+            # calls (ms since the call's first enqueued operation): rows landed, polynomial ready, beam stage done, on host
+            for nch in (1, 2, 4):
+                sync()
+                walls = []
+                for _ in range(6):
+                    t0 = time.perf_counter()
+                    eng.snowfall_batch_host(tid, hp, off, orders, bench.DIV_DEG, host_out=outs[0], device_prepass=True,
+                                            n_chunks=nch)
+                    walls.append((time.perf_counter() - t0) * 1e3)
+                tr = eng.host_pipeline_trace().astype(np.float64).reshape(-1)
+                t = torch.zeros(1 + 16, dtype=torch.float64, device=dev)
+                t[0] = float(np.median(walls[1:]))
+                t[1:1 + tr.size] = torch.from_numpy(tr).to(dev)
+                if world > 1:
+                    g = [torch.zeros_like(t) for _ in range(world)]
+                    dist.all_gather(g, t)
+                else:
+                    g = [t]
+                res[f'sync_chunks{nch}'] = [{'wall_ms': round(float(x[0]), 3),
+                                             'timeline_ms': [round(float(v), 3) for v in x[1:1 + 4 * nch]]} for x in g]
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
