@@ -328,6 +328,11 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
 
+    # e2e leg with several ranks on one box: the host's memory bandwidth is the limiter (tools/e2e_probe_ranks.py), so the
+    # copy-out kernel that moves only the kept rows pays (8 ranks: 5.98 vs 6.84 ms per step); on one GPU the plain D2H copy
+    # is faster (2.06 vs 2.12 ms) and stays the default.  Read by the library when its host pipeline is created.
+    if world > 1:
+        os.environ.setdefault('LSS_PIPE_KERNEL_OUT', '1')
     numa_cpus = None
     if world > 1 and os.environ.get('LSS_NUMA_BIND', '0') == '1':
         try:
@@ -559,11 +564,16 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_sync = float(tt[0].item()), float(tt[1].item())
+        kernel_out = (not fused_wet) and os.environ.get('LSS_PIPE_KERNEL_OUT') == '1'
+        rows_out = N
+        if kernel_out:                                     # only the kept rows travel: count them from the result
+            rows_out = int(host_outs[0]['counts'].sum().item())
         e2e = {'value': points_all / dt, 'unit': 'points/s', 'h2d_bytes_per_step': int(N * 20),
-               'd2h_bytes_per_step': int(N * 20 + B * 4 + (0 if fused_wet else B * 32)), 'ms_per_step': dt * 1e3,
+               'd2h_bytes_per_step': int(rows_out * 20 + B * 4 + (0 if fused_wet else B * 32)), 'ms_per_step': dt * 1e3,
                'steps_timed': n_e2e,
                'sync_call': {'value': points_all / dt_sync, 'ms_per_step': dt_sync * 1e3},
                'chunks': args.e2e_chunks, 'batches_in_flight': depth,
+               'copy_out': 'kept rows by kernel' if kernel_out else 'whole slot by copy engine',
                'host_numa_bound_cpus': None if numa_cpus is None else len(numa_cpus), 'timing': how}
 
     if rank != 0:

@@ -101,6 +101,9 @@ __device__ __forceinline__ double shfl_f64(double v, int src)
     return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
+#ifndef LSS_CLASS_BY_RANGE
+#define LSS_CLASS_BY_RANGE 0
+#endif
 #ifndef LSS_SCAN_CTAS
 #define LSS_SCAN_CTAS 10
 #endif
@@ -259,9 +262,15 @@ __global__ void __launch_bounds__(SNOW_TPB, LSS_SCAN_CTAS) k_scan(DevArgs a)
             base = __shfl_sync(FULL, base, leader);
             hbase = __shfl_sync(FULL, hbase, leader);
             if (push) {
-                // work class: everything a beam costs the solve kernel (occluders, samples) grows with the target range;
-                // the costliest class comes first so that the kernel's tail is cheap tiles
+                // work class = number of occluders (then far / near target): what a beam costs the solve kernel -- claiming,
+                // pulses, the sweep over the window ends -- is per-beam serial work proportional to it, and a warp runs as long as
+                // its slowest lane, so the 32 beams of a tile should have the same count.  The costliest class comes first so
+                // that the kernel's tail is cheap tiles.  (Round 1 sorted by target range: the cost was the window samples then.)
+#if LSS_CLASS_BY_RANGE
                 const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
+#else
+                const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, 2 * min(L, 63) + (d32 > 40.0f ? 1 : 0));
+#endif
                 const int slot = base + __popc(pm & ((1u << lane) - 1u));
                 const int hoff = hbase + lincl - L;
                 const bool fits = hoff + L <= a.hit_cap;        // position array full: the beam goes to the overflow kernel
