@@ -2,7 +2,7 @@
 # 1 GPU: full GPU suite + bench line after a kernel change
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-TAG=${1:-r2s16}
+TAG=${1:-check}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 python - <<PY
