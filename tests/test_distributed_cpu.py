@@ -84,3 +84,49 @@ def test_gloo_world2_sharded_gather(n_clouds):
     assert all(r[1] for r in res), res
     spans = sorted((r[2], r[3]) for r in res)
     assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == n_clouds
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from lidar_snow_sim_b200.distributed import BatchGather
+        n_rows, n_clouds = 50, 3
+        dev = torch.device('cpu')
+        # asking for the push kernel without an engine / off a GPU must fall back to the library all-gather, not fail
+        g = BatchGather(n_rows, n_clouds, dev, depth=2, kind='push')
+        ok = g.kind == 'nccl'
+        for step in range(5):                     # double-buffered: buffer j is reused every second step
+            j = step & 1
+            g.wait(j)
+            pts = torch.full((n_rows, 5), float(100 * step + rank))
+            cnt = torch.full((n_clouds,), 10 * step + rank, dtype=torch.int32)
+            g.start(j, pts, cnt)
+            g.wait(j)
+            for r in range(world):
+                ok &= bool((g.points[j][r * n_rows:(r + 1) * n_rows] == float(100 * step + r)).all())
+                ok &= bool((g.counts[j][r * n_clouds:(r + 1) * n_clouds] == 10 * step + r).all())
+        g.wait_all()
+        q.put((rank, bool(ok)))
+    except Exception as exc:
+        q.put((rank, False, repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_batch_gather_falls_back_to_the_library_all_gather():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
