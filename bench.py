@@ -589,7 +589,7 @@ def main():
     achieved = algo_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
     per_step = {k: (v[0] / max(v[1], 1)) * (v[1] / args.steps) for k, v in ktimes.items() if v[1]}
     roofline = {'bound': 'hbm',
-                'kernel': 'beam stage = k_snowfall<SCAN> (all beams) + k_list_sort + k_solve (dominant: the beams with '
+                'kernel': 'beam stage = k_scan (all beams) + k_list_sort + k_solve (dominant: the beams with '
                           'occluders) + overflow kernel, one CUDA-event pair around the four launches',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(algo_bytes),

@@ -53,7 +53,7 @@ struct DevArgs {
     unsigned long long *att_sum; // [B] sum of their new integer intensities
     int *status;
     // work lists (cloud << 32 | row): the scan kernel defers every beam that has occluders to the dense solve kernel,
-    // which in turn defers beams with more than FAST_CAP occluders to the overflow kernel
+    // which in turn defers beams with more than SOLVE_LCAP occluders to the overflow kernel
     const unsigned long long *list_in;
     const int *count_in;
     int cap_in;
@@ -81,17 +81,10 @@ constexpr int TILE = 1024;                          // rows per scatter tile
 constexpr int NBINS = LSS_N_CHANNELS + 1;           // + "not a valid channel" (sorted last)
 constexpr int POOL = 128;                           // pulses a warp publishes per cooperative batch
 constexpr int CCAP = 512;                           // candidate samples a warp evaluates per cooperative batch
-constexpr int FAST_CAP = 24;                        // occluders per beam held by the fast kernel (mean 1-5)
-constexpr int SLOW_CAP = 128;                       // ... by the overflow kernel
+constexpr int SLOW_CAP = 128;                       // occluders per beam held by the overflow kernel (per-thread lists)
 constexpr int OVF_LIST_CAP = 1 << 16;               // beams the overflow kernel can take per call
-// kernel modes
-constexpr int MODE_SCAN = 0;      // every beam of the batch: candidate scan; beams without occluders are finished here,
-                                  // the others are pushed to the solve list
 constexpr int LIST_HDR_BYTES = 2048;  // ints: [0] solve count, [1] overflow count, [C..2C) class counts, [2C..3C) cursors
-constexpr int LIST_CLASSES = 128;  // solve list is counting-sorted by work class (target range) before the solve kernel
-constexpr int MODE_LIST = 1;      // one listed beam per thread (dense: every lane has occluders): scan again, claim,
-                                  // waveform, finish
-
+constexpr int LIST_CLASSES = 128;  // solve list is counting-sorted by work class (occluder count) before the solve kernel
 
 __device__ __forceinline__ void raise_status(int *status, int code) { atomicMax(status, code); }
 

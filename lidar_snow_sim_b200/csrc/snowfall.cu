@@ -3,14 +3,12 @@
 // Pipeline per call (on the caller's stream; the pre-pass is forked onto an engine side stream and joined before k_keep):
 //   [pre-pass]       ground plane + noise-threshold polynomial (prepass.cu), concurrent with the beam kernels
 //                                                                                 (tools/snowfall/simulation.py:449-467)
-//   k_snowfall<SCAN> one thread per beam, beams in INPUT order: range/azimuth, candidate scan of ONE azimuth bucket of
-//                    the channel's snowflake plane up to the first occluder; un-occluded beams are finished, the others
-//                    pushed to the solve list with a work class (target range)
+//   k_scan           (solve.cu) every beam, rows in INPUT order: range / azimuth, walk of ONE azimuth bucket of the channel's
+//                    snowflake plane; un-occluded beams are finished, the others pushed to the solve list with their hits
 //   k_list_sort      counting sort of the solve list by work class (a solve warp runs as long as its slowest lane)
-//   k_snowfall<LIST> the listed beams: all occluders, exact float64 disk/wedge test, nearest-first claiming of the beam's
-//                    angular sub-intervals; then, warp-cooperatively, the summed sin^2 waveform + argmax; relabel / move
-//                    the point; label-1 statistics                               (simulation.py:50-194, 231-424)
-//   k_snowfall<128>  beams with more than 24 occluders (rare)
+//   k_solve          (solve.cu) the listed beams: nearest-first claiming of the beam's angular sub-intervals, summed
+//                    sin^2 waveform + argmax, relabel / move the point, label-1 statistics  (simulation.py:50-194, 231-424)
+//   k_overflow       beams with more than 63 occluders (rare): one beam per thread, per-thread lists of up to 128 hits
 //   k_keep           threshold (original range) + FOV keep flag, per-tile channel histogram of the kept rows,
 //                    num_attenuated / num_removed                                 (simulation.py:516-540)
 //   k_tile_scan      per cloud: exclusive scan of the tile histograms -> destination of every (tile, channel) run;
@@ -50,13 +48,13 @@ __device__ __noinline__ double waveform_sample(int k, double Rk, int q0, int q1,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// per-beam solve
+// overflow kernel: the beams the solve kernel's shared-memory arena cannot take (more than 63 occluders).  This is round
+// 1's per-beam kernel reduced to its list mode: it walks the bucket again, keeps per-thread lists (local memory) and
+// evaluates whole windows with a sinpi per sample -- slow, general, and only ever run on a handful of beams.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int CAP, int MODE>
-__global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB) k_snowfall(DevArgs a)
+__global__ void __launch_bounds__(SNOW_TPB, 1) k_overflow(DevArgs a)
 {
-    constexpr bool SLOW = MODE == MODE_LIST;        // listed beams: unrelated rows per lane, scattered I/O
-    __shared__ float s_rows[SNOW_WARPS][32 * 5];                   // per-warp coalesced staging of 32 rows (in and out)
+    constexpr int CAP = SLOW_CAP;
     __shared__ double s_amp[SNOW_WARPS][POOL];
     __shared__ double s_r[SNOW_WARPS][POOL];
     __shared__ int s_win[SNOW_WARPS][POOL];
@@ -65,50 +63,19 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
     __shared__ int s_kbest[SNOW_WARPS][32];
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // fast kernel: block (x, y) = 128 consecutive rows of cloud y.  Overflow kernel: one listed beam per thread, the
-    // lanes of a warp may belong to different clouds.
-    int b, i, blk0 = 0;
-    bool active;
-    if (SLOW) {
-        const int slot = blockIdx.x * SNOW_TPB + threadIdx.x;
-        const int cnt = min(*a.count_in, a.cap_in);
-        if (blockIdx.x * SNOW_TPB >= cnt) return;
-        active = slot < cnt;
-        const unsigned long long it = active ? a.list_in[slot] : 0ull;
-        b = (int)((it >> 32) & 0xffffu);
-        i = (int)(it & 0xffffffffu);
-    } else {
-        b = blockIdx.y;
-        blk0 = blockIdx.x * SNOW_TPB;
-        i = blk0 + threadIdx.x;
-    }
+    // one listed beam per thread: the lanes of a warp may belong to different clouds
+    const int slot = blockIdx.x * SNOW_TPB + threadIdx.x;
+    const int cnt = min(*a.count_in, a.cap_in);
+    if (blockIdx.x * SNOW_TPB >= cnt) return;
+    const bool active = slot < cnt;
+    const unsigned long long it = active ? a.list_in[slot] : 0ull;
+    const int b = (int)((it >> 32) & 0xffffu);
+    const int i = (int)(it & 0xffffffffu);
     const int64_t beg = a.cloud_off[b];
-    const int n = (int)(a.cloud_off[b + 1] - beg);
-    if (!SLOW) {
-        if (blk0 >= n) return;
-        active = i < n;
-    }
-    const int w0 = blk0 + 32 * wid;                                 // first row of this warp
-    const int nf_w = SLOW ? 0 : max(0, min(32, n - w0)) * 5;        // floats of this warp's rows
     float px = 0, py = 0, pz = 0, pint = 0, pch = 0;
-    if (SLOW) {
-        if (active) {
-            const float *row = a.pts + (beg + i) * 5;
-            px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
-        }
-    } else {
-        // coalesced load of the warp's 32 rows (160 floats); no block-wide barrier anywhere in this kernel
-        const float *src = a.pts + (beg + w0) * 5;
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-            const int f = q * 32 + lane;
-            if (f < nf_w) s_rows[wid][f] = __ldcs(src + f);     // streamed once: do not displace the table index in L2
-        }
-        __syncwarp();
-        if (active) {
-            const float *row = &s_rows[wid][5 * lane];
-            px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
-        }
+    if (active) {
+        const float *row = a.pts + (beg + i) * 5;
+        px = row[0]; py = row[1]; pz = row[2]; pint = row[3]; pch = row[4];
     }
     // np.linalg.norm([x, y, z], axis=0) in float32: sqrt((x*x + y*y) + z*z), no FMA   (simulation.py:89)
     const float d32 = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
@@ -123,7 +90,7 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
     // per-beam lists (local memory): hits (a1, a2, range) -> after claiming: pulses (amplitude, range, window)
     double ha1[CAP + 1], ha2[CAP], hr[CAP + 1];
     int ks[CAP + 1], ke[CAP + 1];
-    bool deferred = false;       // fast kernel only: too many occluders, the overflow kernel redoes this beam
+    bool deferred = false;       // only with a further overflow list (a.list_out): not used by the engine's launcher
     int n_pulses = 0;            // > 0: this beam has a waveform to solve (claiming particles + hard target)
 
     if (active && ch < LSS_N_CHANNELS) {
@@ -168,7 +135,6 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
                 const bool right_hit = within(right - phi, alpha);
                 const bool left_hit = within(left - phi, alpha);
                 if (!(inside || right_hit || left_hit)) continue;
-                if (MODE == MODE_SCAN) { L = 1; break; }           // one occluder is enough to defer the beam
                 if (L == CAP) { overflow = true; break; }
                 const double a1 = right_hit ? right : a.tan[pi].t_right;   // geometry.py:26-27
                 const double a2 = left_hit ? left : a.tan[pi].t_left;
@@ -179,7 +145,6 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
                 L++;
             }
         }
-        if (MODE == MODE_SCAN) overflow = false;          // the scan kernel only needs to know whether L > 0
         if (overflow) {
             if (a.list_out == nullptr) {
                 raise_status(a.status, LSS_ERR_OCCLUDER_OVERFLOW);
@@ -190,28 +155,7 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
                 deferred = slot < a.cap_out;
             }
         }
-        if (MODE == MODE_SCAN) {
-            // defer every beam with occluders (warp-aggregated push: the solve kernel's warps get neighbouring beams)
-            const bool push = L > 0;
-            const unsigned pm = __ballot_sync(__activemask(), push);
-            if (push) {
-                int base = 0;
-                const int leader = __ffs(pm) - 1;
-                if (lane == leader) base = atomicAdd(a.count_out, __popc(pm));
-                base = __shfl_sync(pm, base, leader);
-                // work class of the beam: everything it costs the solve kernel (bucket prefix, occluders, samples)
-                // grows with the target range
-                // grows with the target range; the costliest class comes first so that the kernel's tail is cheap CTAs
-                const int cls = LIST_CLASSES - 1 - min(LIST_CLASSES - 1, (int)(d32 * (LIST_CLASSES / 100.0f)));
-                a.list_out[base + __popc(pm & ((1u << lane) - 1u))] =
-                    ((unsigned long long)cls << 48) | ((unsigned long long)b << 32) | (unsigned)i;
-                const unsigned cm = __match_any_sync(pm, cls);
-                if (lane == __ffs(cm) - 1) atomicAdd(a.count_out + LIST_CLASSES + cls, __popc(cm));
-                deferred = true;
-            }
-        }
-
-        if (MODE != MODE_SCAN && L > 0 && !overflow) {
+        if (L > 0 && !overflow) {
             // ---- compute_occlusion_dict (simulation.py:231-295) ---------------------------------------------------
             // The reference splits the beam into elementary sub-intervals between all sorted end points and lets the
             // particles claim, nearest first, every still-unclaimed piece inside their own interval.  Equivalent
@@ -326,10 +270,10 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
         }
     };
     int T_all = 0;
-    if (MODE != MODE_SCAN && n_pulses > 0) for_each_segment([&](int k_lo, int k_hi, int, int) { T_all += k_hi - k_lo; });
+    if (n_pulses > 0) for_each_segment([&](int k_lo, int k_hi, int, int) { T_all += k_hi - k_lo; });
     double best = 0.0;
     int kbest = 0;
-    bool coop = MODE != MODE_SCAN && n_pulses > 0;
+    bool coop = n_pulses > 0;
     if (T_all > CCAP || n_pulses > POOL) {   // pathological beam (dozens of overlapping pulses): solve it in this thread
         coop = false;
         for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
@@ -342,75 +286,73 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
     }
     s_best[wid][lane] = 0.0;
     s_kbest[wid][lane] = 0;
-    if (MODE != MODE_SCAN) {
-        unsigned remaining = __ballot_sync(0xffffffffu, coop);
-        while (remaining) {
-            const bool rem = (remaining >> lane) & 1u;
-            const int mine = rem ? n_pulses : 0, myT = rem ? T_all : 0;
-            int incl = mine, cincl = myT;
+    unsigned remaining = __ballot_sync(0xffffffffu, coop);
+    while (remaining) {
+        const bool rem = (remaining >> lane) & 1u;
+        const int mine = rem ? n_pulses : 0, myT = rem ? T_all : 0;
+        int incl = mine, cincl = myT;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, s);
-                const int u = __shfl_up_sync(0xffffffffu, cincl, s);
-                if (lane >= s) { incl += t; cincl += u; }
-            }
-            // a prefix of the remaining lanes (each has <= 49 pulses and <= CCAP candidates)
-            const bool in_batch = rem && incl <= POOL && cincl <= CCAP;
-            const unsigned batch = __ballot_sync(0xffffffffu, in_batch);
-            remaining &= ~batch;
-            const int total = __shfl_sync(0xffffffffu, cincl, 31 - __clz(batch));
-            if (in_batch) {
-                const int poff = incl - mine;
-                int coff = cincl - myT;
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, s);
+            const int u = __shfl_up_sync(0xffffffffu, cincl, s);
+            if (lane >= s) { incl += t; cincl += u; }
+        }
+        // a prefix of the remaining lanes (each has <= 49 pulses and <= CCAP candidates)
+        const bool in_batch = rem && incl <= POOL && cincl <= CCAP;
+        const unsigned batch = __ballot_sync(0xffffffffu, in_batch);
+        remaining &= ~batch;
+        const int total = __shfl_sync(0xffffffffu, cincl, 31 - __clz(batch));
+        if (in_batch) {
+            const int poff = incl - mine;
+            int coff = cincl - myT;
 #pragma unroll 1
-                for (int j = 0; j < mine; j++) {
-                    s_amp[wid][poff + j] = ha1[j];
-                    s_r[wid][poff + j] = hr[j];
-                    s_win[wid][poff + j] = ks[j] | (ke[j] << 16);
-                }
-                for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
-                    const unsigned hi_bits = ((unsigned)(poff + j0) << 11) | ((unsigned)(poff + j1) << 18) | ((unsigned)lane << 25);
+            for (int j = 0; j < mine; j++) {
+                s_amp[wid][poff + j] = ha1[j];
+                s_r[wid][poff + j] = hr[j];
+                s_win[wid][poff + j] = ks[j] | (ke[j] << 16);
+            }
+            for_each_segment([&](int k_lo, int k_hi, int j0, int j1) {
+                const unsigned hi_bits = ((unsigned)(poff + j0) << 11) | ((unsigned)(poff + j1) << 18) | ((unsigned)lane << 25);
 #pragma unroll 4
-                    for (int k = k_lo; k < k_hi; k++) s_cand[wid][coff++] = (unsigned)k | hi_bits;
-                });
-            }
-            __syncwarp();
-            for (int base = 0; base < total; base += 32) {
-                const int c = base + lane;
-                int owner = -1, k = 0;
-                double v = 0.0;
-                if (c < total) {
-                    const unsigned desc = s_cand[wid][c];
-                    k = desc & 2047u;
-                    owner = desc >> 25;
-                    const int q0 = (desc >> 11) & 127u, q1 = (desc >> 18) & 127u;
-                    const double Rk = __ldg(&a.R[k]);
+                for (int k = k_lo; k < k_hi; k++) s_cand[wid][coff++] = (unsigned)k | hi_bits;
+            });
+        }
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int c = base + lane;
+            int owner = -1, k = 0;
+            double v = 0.0;
+            if (c < total) {
+                const unsigned desc = s_cand[wid][c];
+                k = desc & 2047u;
+                owner = desc >> 25;
+                const int q0 = (desc >> 11) & 127u, q1 = (desc >> 18) & 127u;
+                const double Rk = __ldg(&a.R[k]);
 #pragma unroll 1
-                    for (int q = q0; q <= q1; q++) {
-                        const int wn = s_win[wid][q];
-                        if (k >= (wn & 0xffff) && k < (wn >> 16)) {
-                            // sin(pi (R - r) / (c tau)) of simulation.py:549, as sinpi of the normalised offset
-                            const double sn = sinpi((Rk - s_r[wid][q]) * inv_ctau);
-                            v += s_amp[wid][q] * (sn * sn);      // pulses in dict order, like the reference's i[k] +=
-                        }
+                for (int q = q0; q <= q1; q++) {
+                    const int wn = s_win[wid][q];
+                    if (k >= (wn & 0xffff) && k < (wn >> 16)) {
+                        // sin(pi (R - r) / (c tau)) of simulation.py:549, as sinpi of the normalised offset
+                        const double sn = sinpi((Rk - s_r[wid][q]) * inv_ctau);
+                        v += s_amp[wid][q] * (sn * sn);      // pulses in dict order, like the reference's i[k] +=
                     }
                 }
-                // per-beam argmax over the lanes holding candidates of the same beam: peer groups by beam, then three
-                // integer reductions (non-negative doubles order like their bit patterns): max high word, max low word
-                // among those, min sample index among the exact ties -> the first maximum, like np.argmax
-                const unsigned peers = __match_any_sync(0xffffffffu, owner);
-                const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
-                const unsigned vhi = (unsigned)(vb >> 32), vlo = (unsigned)vb;
-                const unsigned mhi = __reduce_max_sync(peers, vhi);
-                const unsigned mlo = __reduce_max_sync(peers, vhi == mhi ? vlo : 0u);
-                const bool is_max = (vhi == mhi) && (vlo == mlo);
-                const unsigned kmin = __reduce_min_sync(peers, is_max ? (unsigned)k : 0xffffffffu);
-                if (owner >= 0 && lane == __ffs(peers) - 1) {
-                    const double vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-                    if (vmax > s_best[wid][owner]) { s_best[wid][owner] = vmax; s_kbest[wid][owner] = (int)kmin; }
-                }
-                __syncwarp();
             }
+            // per-beam argmax over the lanes holding candidates of the same beam: peer groups by beam, then three
+            // integer reductions (non-negative doubles order like their bit patterns): max high word, max low word
+            // among those, min sample index among the exact ties -> the first maximum, like np.argmax
+            const unsigned peers = __match_any_sync(0xffffffffu, owner);
+            const unsigned long long vb = (unsigned long long)__double_as_longlong(v);
+            const unsigned vhi = (unsigned)(vb >> 32), vlo = (unsigned)vb;
+            const unsigned mhi = __reduce_max_sync(peers, vhi);
+            const unsigned mlo = __reduce_max_sync(peers, vhi == mhi ? vlo : 0u);
+            const bool is_max = (vhi == mhi) && (vlo == mlo);
+            const unsigned kmin = __reduce_min_sync(peers, is_max ? (unsigned)k : 0xffffffffu);
+            if (owner >= 0 && lane == __ffs(peers) - 1) {
+                const double vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+                if (vmax > s_best[wid][owner]) { s_best[wid][owner] = vmax; s_kbest[wid][owner] = (int)kmin; }
+            }
+            __syncwarp();
         }
     }
     if (coop) {
@@ -450,49 +392,20 @@ __global__ void __launch_bounds__(SNOW_TPB, CAP > FAST_CAP ? 1 : 1024 / SNOW_TPB
         if (!deferred && a.nocc) a.nocc[beg + i] = n_claim;
     }
     const bool counted = active && !deferred;      // a deferred beam is accounted for by the overflow kernel
-    if (SLOW) {
-        // one unrelated beam per thread: plain stores; integer atomics aggregated over lanes hitting the same counter
-        if (counted) {
-            float *row = a.aug + (beg + i) * 5;
-            row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
-        }
-        {
-            const bool on = counted && att_new_i >= 0;
-            const int key = b * LSS_N_CHANNELS + (ch < LSS_N_CHANNELS ? ch : 0);
-            const unsigned mk = __match_any_sync(0xffffffffu, on ? key : -1);
-            if (on && lane == __ffs(mk) - 1) atomicAdd(a.att_cnt + key, (unsigned)__popc(mk));
-            const unsigned m = __match_any_sync(0xffffffffu, on ? b : -1);
-            const unsigned sum = __reduce_add_sync(m, on ? (unsigned)att_new_i : 0u);
-            if (on && lane == __ffs(m) - 1) atomicAdd(&a.att_sum[b], (unsigned long long)sum);
-        }
-        return;
-    }
-    // augmented rows back through shared memory (coalesced store)
-    __syncwarp();
-    if (active) {
-        float *row = &s_rows[wid][5 * lane];
+    // one unrelated beam per thread: plain stores; integer atomics aggregated over lanes hitting the same counter
+    if (counted) {
+        float *row = a.aug + (beg + i) * 5;
         row[0] = out_x; row[1] = out_y; row[2] = out_z; row[3] = out_i; row[4] = out_l;
-    }
-    __syncwarp();
-    {
-        float *dst = a.aug + (beg + w0) * 5;
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-            const int f = q * 32 + lane;
-            if (f < nf_w) dst[f] = s_rows[wid][f];              // read back by k_keep / k_scatter from L2
-        }
     }
     // label-1 beams per channel and the sum of their new intensities (simulation.py:170): integer atomics, order
     // independent => bit-reproducible
-    {
-        const int ca = (counted && att_new_i >= 0) ? ch : -1;
-        const unsigned ma = __match_any_sync(0xffffffffu, ca);
-        if (ca >= 0 && lane == __ffs(ma) - 1) atomicAdd(&a.att_cnt[b * LSS_N_CHANNELS + ca], (unsigned)__popc(ma));
-        unsigned long long sn = ca >= 0 ? (unsigned long long)att_new_i : 0ull;
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) sn += __shfl_xor_sync(0xffffffffu, sn, s);
-        if (lane == 0 && sn) atomicAdd(&a.att_sum[b], sn);
-    }
+    const bool on = counted && att_new_i >= 0;
+    const int key = b * LSS_N_CHANNELS + (ch < LSS_N_CHANNELS ? ch : 0);
+    const unsigned mk = __match_any_sync(0xffffffffu, on ? key : -1);
+    if (on && lane == __ffs(mk) - 1) atomicAdd(a.att_cnt + key, (unsigned)__popc(mk));
+    const unsigned m = __match_any_sync(0xffffffffu, on ? b : -1);
+    const unsigned sum = __reduce_add_sync(m, on ? (unsigned)att_new_i : 0u);
+    if (on && lane == __ffs(m) - 1) atomicAdd(&a.att_sum[b], (unsigned long long)sum);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -944,7 +857,7 @@ lss_status lss_snowfall_run(lss_engine *e, const SnowfallArgs &s, cudaStream_t s
         // 3. overflow: beams with more occluders than the solve kernel's arena takes per beam (rare), round-1 list kernel
         a.list_in = d_ovf_list; a.count_in = d_counts2 + 1; a.cap_in = OVF_LIST_CAP;
         a.list_out = nullptr; a.count_out = nullptr; a.cap_out = 0;
-        k_snowfall<SLOW_CAP, MODE_LIST><<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
+        k_overflow<<<OVF_LIST_CAP / SNOW_TPB, SNOW_TPB, 0, stream>>>(a);
         e->launches += 1;           // (+ one each from the three KernelTimer brackets = 4 launches)
     }
     if (ev_join) LSS_CUDA_CHECK(e, cudaStreamWaitEvent(stream, ev_join, 0));

@@ -30,7 +30,7 @@
 //     all 32 beams are handled one per lane, with uniform code.
 //
 // Beams the arena cannot take (more than SOLVE_LCAP occluders) go to the overflow list and are redone by the
-// round-1 list kernel (snowfall.cu, k_snowfall<SLOW_CAP, MODE_LIST>), which has no such limit below 128.
+// overflow kernel (snowfall.cu, k_overflow: round 1's list kernel), which has no such limit below 128.
 #include "beam.cuh"
 
 namespace {

@@ -15,7 +15,7 @@ grep -E "passed|failed|RACECHECK SUMMARY" gpurun_out/r2g_racecheck.log | head -5
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r2g_bench.json 2> gpurun_out/r2g_bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --steps 20 --warmup 5 --config 2 --no-cpu-baseline > gpurun_out/r2g_bench_cfg2.json 2> gpurun_out/r2g_bench_cfg2.err; echo "bench cfg2 rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 100 --csv --log-file gpurun_out/r2g_launches.csv python tools/profile_step.py --steps 10 > gpurun_out/r2g_ncu_list.log 2>&1; echo "list rc=$?"
-timeout 400 ncu --set full --clock-control none --import-source on -k "regex:k_scan|k_list_sort|k_solve|k_snowfall" -s 16 -c 4 -f -o gpurun_out/r2g_beam python tools/profile_step.py --steps 6 > gpurun_out/r2g_ncu_beam.log 2>&1; echo "ncu beam rc=$?"
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:k_scan|k_list_sort|k_solve|k_overflow" -s 16 -c 4 -f -o gpurun_out/r2g_beam python tools/profile_step.py --steps 6 > gpurun_out/r2g_ncu_beam.log 2>&1; echo "ncu beam rc=$?"
 python - <<'PY'
 import json
 for f in ('gpurun_out/r2g_bench.json', 'gpurun_out/r2g_bench_cfg2.json'):

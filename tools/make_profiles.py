@@ -1,7 +1,7 @@
 """Turn the raw ncu artefacts a gpurun call left in gpurun_out/ into the tracked summaries under profiles/.
     python tools/make_profiles.py <tag> <launches.csv> <beam.ncu-rep> [bench.json ...]
 
-<beam.ncu-rep>: `ncu --set full -k "regex:k_scan|k_list_sort|k_solve|k_snowfall" -c 4`: the four launches of the beam stage
+<beam.ncu-rep>: `ncu --set full -k "regex:k_scan|k_list_sort|k_solve|k_overflow" -c 4`: the four launches of the beam stage
 of one step (scan, list sort, solve, overflow)."""
 import csv
 import json
@@ -63,9 +63,9 @@ def to_bytes(unit, val):
 traffic = 0.0
 per_launch = []
 with open(os.path.join(out_dir, f'{tag}_beam_stage_ncu.txt'), 'w') as f:
-    f.write('# ncu --set full --clock-control none --import-source on -k "regex:k_scan|k_list_sort|k_solve|k_snowfall" -s 16 -c 4\n')
+    f.write('# ncu --set full --clock-control none --import-source on -k "regex:k_scan|k_list_sort|k_solve|k_overflow" -s 16 -c 4\n')
     f.write('#     python tools/profile_step.py --steps 6\n')
-    f.write('# the four launches of the beam stage of one step: k_scan, k_list_sort, k_solve (dominant), k_snowfall<128,1> overflow\n')
+    f.write('# the four launches of the beam stage of one step: k_scan, k_list_sort, k_solve (dominant), k_overflow\n')
     for v in rr[2:]:
         if len(v) != len(h):
             continue
