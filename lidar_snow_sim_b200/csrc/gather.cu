@@ -126,7 +126,7 @@ extern "C" lss_status lss_gather_push(lss_engine *e, const float *d_points, cons
     }
     a.mc = d_mc_points; a.mc_counts = d_mc_counts;
     // Measured on 8 GPUs next to the beam kernels (profiles/r02_n8c_*, r02_n8d_*): multicast 37 CTAs 1.09-1.13 ms per step,
-    // 74 / 148 CTAs 1.22 / 1.34 ms (the partition is static: the last CTA to find an SM slot sets the duration); per-peer
+    // 74 / 148 CTAs 1.22 / 1.34 ms (alone every count takes 0.70 ms); per-peer
     // stores 64 CTAs 1.07 ms, 148 CTAs 1.57 ms.  A chunk-cursor variant with 148 CTAs was slower on 2 GPUs (0.97 vs 0.93 ms);
     // four instead of two 16-byte loads in flight per thread (multicast) changed nothing on 2 GPUs and was slower on 8 (1.28 ms).
     if (n_blocks <= 0) n_blocks = d_mc_points ? std::max(1, e->n_sm / 4) : std::min(e->n_sm, 64);
