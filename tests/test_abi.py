@@ -77,3 +77,44 @@ def test_focal_offset_matches_python():
     for v in fd:
         t = 1 - (v * 100) / 13100
         assert (1 - v * 100 / 13100) ** 2 == t * t          # simulation.py:76: pow(x, 2) == x*x for these values
+
+
+def _header_params(name):
+    txt = open(os.path.join(ROOT, 'include', 'lidar_snow_sim.h')).read()
+    m = re.search(r'LSS_API[^;(]*?\b' + name + r'\s*\(([^;]*?)\)\s*;', txt, re.S)
+    assert m, name
+    return [p.strip() for p in m.group(1).split(',') if p.strip()]
+
+
+def _call_args(text, call):
+    """Arguments of the first `call(...)` in text (nesting aware, comments stripped)."""
+    i = text.index(call + '(') + len(call) + 1
+    depth, args, cur = 1, [], ''
+    body = re.sub(r'#[^\n]*|/\*.*?\*/', '', text[i:], flags=re.S)
+    for ch in body:
+        if ch in '([':
+            depth += 1
+        elif ch in ')]':
+            depth -= 1
+            if depth == 0:
+                break
+        if ch == ',' and depth == 1:
+            args.append(cur.strip())
+            cur = ''
+        else:
+            cur += ch
+    args.append(cur.strip())
+    return [a for a in args if a]
+
+
+def test_signatures_and_documented_calls_have_the_header_arity():
+    """ctypes argtypes and the raw C-ABI examples of INTEGRATION.md follow the header's parameter lists."""
+    from lidar_snow_sim_b200 import _lib
+    for name, _, argtypes in _lib.SIGNATURES:
+        params = _header_params(name)
+        n = 0 if params == ['void'] else len(params)
+        assert n == len(argtypes), f'{name}: header has {n} parameters, _lib.SIGNATURES {len(argtypes)}'
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    for call, name in (('L.lss_snowfall_batch', 'lss_snowfall_batch'),
+                       ('\nlss_snowfall_batch_host_submit', 'lss_snowfall_batch_host_submit')):
+        assert len(_call_args(doc, call)) == len(_header_params(name)), f'INTEGRATION.md: {name} example is out of date'
